@@ -1,0 +1,290 @@
+"""ctypes binding of include/dvins_perception.h (Python host side; no torch types cross the boundary).
+
+The library is REQUIRED: importing this module raises if libdvins_b200.so is missing, and
+``Engine(...)`` raises ``DvError`` (DV_ERR_NOGPU) when no sm_100 GPU is visible - there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdvins_b200.so")
+
+DESC_DIM = 256
+GLOBAL_DIM = 512
+
+STATUS = {0: "DV_OK", 1: "DV_ERR_INVALID", 2: "DV_ERR_CUDA", 3: "DV_ERR_UNSUPPORTED", 4: "DV_ERR_WEIGHTS",
+          5: "DV_ERR_CAPACITY", 6: "DV_ERR_COMM", 7: "DV_ERR_NOGPU"}
+
+
+class DvConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+                ("max_batch", C.c_int32), ("max_kpts", C.c_int32), ("nms_radius", C.c_int32),
+                ("det_thresh", C.c_float), ("border", C.c_int32), ("max_vio", C.c_int32), ("knn_k", C.c_int32),
+                ("exclude_recent", C.c_int32), ("lg_filter_thresh", C.c_float), ("lg_max_kpts", C.c_int32),
+                ("bank_capacity", C.c_int64), ("store_capacity", C.c_int32), ("world_size", C.c_int32),
+                ("rank", C.c_int32), ("weights_path", C.c_char_p)]
+
+
+class DvError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("%s: %s" % (STATUS.get(status, status), msg))
+        self.status = status
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libdvins_b200.so not built (run `python -m d_vins_b200.build`); no fallback exists")
+    return C.CDLL(LIB_PATH)
+
+
+_lib = load_library()
+_lib.dv_last_error.restype = C.c_char_p
+_lib.dv_version.restype = C.c_char_p
+_lib.dv_config_default.restype = None
+
+
+def _ptr(a, ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _chk(rc):
+    if rc != 0:
+        raise DvError(rc, (_lib.dv_last_error() or b"").decode())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def default_config(**kw) -> DvConfig:
+    cfg = DvConfig()
+    _lib.dv_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        if k == "weights_path" and v is not None:
+            v = os.fsencode(v)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _chk(_lib.dv_comm_unique_id(buf))
+    return buf.raw
+
+
+class Engine:
+    """Owns one dv_engine.  Methods mirror the C entry points 1:1 with numpy arrays."""
+
+    def __init__(self, **kw):
+        self.cfg = default_config(**kw)
+        self._h = C.c_void_p()
+        _chk(_lib.dv_create(C.byref(self.cfg), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.dv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- per-keyframe API
+    def frame_upload(self, img: np.ndarray):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        ch = 1 if img.ndim == 2 else img.shape[2]
+        _chk(_lib.dv_frame_upload(self._h, _ptr(img, C.c_uint8), h, w, w * ch, ch))
+
+    def sp_detect(self):
+        k = self.cfg.max_kpts
+        kp = np.zeros((k, 2), np.int32); sc = np.zeros((k,), np.float32)
+        de = np.zeros((k, DESC_DIM), np.float32); kn = np.zeros((k, 2), np.float32)
+        n = C.c_int32(0)
+        _chk(_lib.dv_sp_detect(self._h, _ptr(kp, C.c_int32), _ptr(sc, C.c_float), _ptr(de, C.c_float),
+                               _ptr(kn, C.c_float), C.byref(n)))
+        n = n.value
+        return {"kpts": kp[:n], "scores": sc[:n], "desc": de[:n], "kpts_norm": kn[:n]}
+
+    def sp_describe(self, kpts_xy: np.ndarray):
+        k = _f32(kpts_xy)
+        n = k.shape[0]
+        de = np.zeros((n, DESC_DIM), np.float32)
+        _chk(_lib.dv_sp_describe(self._h, _ptr(k, C.c_float), n, _ptr(de, C.c_float)))
+        return de
+
+    def mix_describe(self):
+        d = np.zeros((GLOBAL_DIM,), np.float32)
+        _chk(_lib.dv_mix_describe(self._h, _ptr(d, C.c_float)))
+        return d
+
+    def bank_append(self, des):
+        d = _f32(des); row = C.c_int64(-1)
+        _chk(_lib.dv_bank_append(self._h, _ptr(d, C.c_float), C.byref(row)))
+        return row.value
+
+    def bank_size(self):
+        r = C.c_int64(0)
+        _chk(_lib.dv_bank_size(self._h, C.byref(r)))
+        return r.value
+
+    def bank_import(self, bank):
+        b = _f32(bank)
+        _chk(_lib.dv_bank_import(self._h, _ptr(b, C.c_float), C.c_int64(b.shape[0])))
+
+    def bank_export(self):
+        n = self.bank_size()
+        out = np.zeros((max(n, 1), GLOBAL_DIM), np.float32); rows = C.c_int64(0)
+        _chk(_lib.dv_bank_export(self._h, _ptr(out, C.c_float), C.c_int64(out.shape[0]), C.byref(rows)))
+        return out[:rows.value]
+
+    def bank_search(self, q, nb_limit, k=None):
+        k = k or self.cfg.knn_k
+        q = _f32(q); D = np.zeros((k,), np.float32); I = np.zeros((k,), np.int64)
+        _chk(_lib.dv_bank_search(self._h, _ptr(q, C.c_float), C.c_int64(nb_limit), k, _ptr(D, C.c_float),
+                                 _ptr(I, C.c_int64)))
+        return D, I
+
+    def lg_match(self, kpts0, kpts1, desc0, desc1, h0, w0, h1, w1, want_mkpts=False):
+        k0, k1, d0, d1 = _f32(kpts0), _f32(kpts1), _f32(desc0), _f32(desc1)
+        m, n = k0.shape[0], k1.shape[0]
+        cap = max(1, min(m, n))
+        ma = np.zeros((cap, 2), np.int32); ms = np.zeros((cap,), np.float32)
+        mk0 = np.zeros((cap, 2), np.float32) if want_mkpts else None
+        mk1 = np.zeros((cap, 2), np.float32) if want_mkpts else None
+        ko = C.c_int32(0)
+        _chk(_lib.dv_lg_match(self._h, _ptr(k0, C.c_float), m, _ptr(k1, C.c_float), n, _ptr(d0, C.c_float),
+                              _ptr(d1, C.c_float), h0, w0, h1, w1, _ptr(ma, C.c_int32), _ptr(ms, C.c_float),
+                              _ptr(mk0, C.c_float), _ptr(mk1, C.c_float), C.byref(ko)))
+        k = ko.value
+        if want_mkpts:
+            return ma[:k], ms[:k], mk0[:k], mk1[:k]
+        return ma[:k], ms[:k]
+
+    # ---------------------------------------------------------------- batched API
+    def batch_upload(self, imgs: np.ndarray):
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        b, h, w = imgs.shape[:3]
+        _chk(_lib.dv_batch_upload(self._h, b, _ptr(imgs, C.c_uint8), C.c_int64(h * w), w))
+
+    def batch_upload_ptr(self, b, ptr, frame_stride, stride):
+        """Raw-pointer variant (e.g. a pinned torch tensor's data_ptr()) - avoids numpy copies in timed loops."""
+        _chk(_lib.dv_batch_upload(self._h, b, C.cast(ptr, C.POINTER(C.c_uint8)), C.c_int64(frame_stride), stride))
+
+    def batch_extract(self, vio_xy, n_vio, frame_ids):
+        v = _f32(vio_xy); nv = np.ascontiguousarray(n_vio, dtype=np.int32)
+        ids = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        b = ids.shape[0]
+        assert v.shape == (b, self.cfg.max_vio, 2), v.shape
+        _chk(_lib.dv_batch_extract(self._h, b, _ptr(v, C.c_float), _ptr(nv, C.c_int32), _ptr(ids, C.c_int64)))
+
+    def batch_commit(self, b):
+        r = C.c_int64(-1)
+        _chk(_lib.dv_batch_commit(self._h, b, C.byref(r)))
+        return r.value
+
+    def batch_search(self, nb_limit):
+        nb = np.ascontiguousarray(nb_limit, dtype=np.int64)
+        b = nb.shape[0]; k = self.cfg.knn_k
+        D = np.zeros((b, k), np.float32); I = np.zeros((b, k), np.int64)
+        _chk(_lib.dv_batch_search(self._h, b, _ptr(nb, C.c_int64), _ptr(D, C.c_float), _ptr(I, C.c_int64)))
+        return D, I
+
+    def batch_match(self, query_ids, old_ids):
+        q = np.ascontiguousarray(query_ids, dtype=np.int64); o = np.ascontiguousarray(old_ids, dtype=np.int64)
+        b = q.shape[0]; cap = self.cfg.max_vio
+        ma = np.zeros((b, cap, 2), np.int32); ms = np.zeros((b, cap), np.float32); ko = np.zeros((b,), np.int32)
+        _chk(_lib.dv_batch_match(self._h, b, _ptr(q, C.c_int64), _ptr(o, C.c_int64), _ptr(ma, C.c_int32),
+                                 _ptr(ms, C.c_float), _ptr(ko, C.c_int32)))
+        return [(ma[i, :ko[i]], ms[i, :ko[i]]) for i in range(b)]
+
+    def store_read(self, frame_id):
+        cap = self.cfg.max_kpts + self.cfg.max_vio
+        kp = np.zeros((cap, 2), np.float32); de = np.zeros((cap, DESC_DIM), np.float32)
+        n = C.c_int32(0); nsp = C.c_int32(0)
+        _chk(_lib.dv_store_read(self._h, C.c_int64(frame_id), _ptr(kp, C.c_float), _ptr(de, C.c_float),
+                                C.byref(n), C.byref(nsp)))
+        return kp[:n.value], de[:n.value], nsp.value
+
+    def batch_read_global(self, i):
+        d = np.zeros((GLOBAL_DIM,), np.float32)
+        _chk(_lib.dv_batch_read_global(self._h, i, _ptr(d, C.c_float)))
+        return d
+
+    def comm_init(self, uid: bytes):
+        _chk(_lib.dv_comm_init(self._h, C.c_char_p(uid)))
+
+    # ---------------------------------------------------------------- measurement
+    def timer_start(self):
+        _chk(_lib.dv_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        _chk(_lib.dv_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        _chk(_lib.dv_sync(self._h))
+
+    def stats_enable(self, on=True):
+        _chk(_lib.dv_stats_enable(self._h, 1 if on else 0))
+
+    def stats_reset(self):
+        _chk(_lib.dv_stats_reset(self._h))
+
+    def stats_read(self):
+        ms = (C.c_double * 6)(); n = C.c_int64(0)
+        _chk(_lib.dv_stats_read(self._h, ms, C.byref(n)))
+        names = ["sp_convs", "sp_post", "mixvpr", "knn", "lightglue", "copies"]
+        return dict(zip(names, list(ms))), n.value
+
+    # ---------------------------------------------------------------- stage-level
+    def dbg_gemm(self, A, B, bias=None, relu=False):
+        A, B = _f32(A), _f32(B)
+        M, K = A.shape; N = B.shape[0]
+        D = np.zeros((M, N), np.float32)
+        bp = _f32(bias) if bias is not None else None
+        _chk(_lib.dv_dbg_gemm(self._h, _ptr(A, C.c_float), _ptr(B, C.c_float), _ptr(bp, C.c_float), M, N, K,
+                              int(relu), _ptr(D, C.c_float)))
+        return D
+
+    def dbg_conv3x3(self, x_nhwc, w_oihw, bias=None, relu=False, pool=False):
+        x, w = _f32(x_nhwc), _f32(w_oihw)
+        n, h, wd, cin = x.shape; cout = w.shape[0]
+        ho, wo = (h // 2, wd // 2) if pool else (h, wd)
+        y = np.zeros((n, ho, wo, cout), np.float32)
+        bp = _f32(bias) if bias is not None else None
+        _chk(_lib.dv_dbg_conv3x3(self._h, _ptr(x, C.c_float), _ptr(w, C.c_float), _ptr(bp, C.c_float), n, h, wd, cin,
+                                 cout, int(relu), int(pool), _ptr(y, C.c_float)))
+        return y
+
+    def dbg_nms_select(self, score_map):
+        s = _f32(score_map); h8, w8 = s.shape
+        nms = np.zeros_like(s); k = self.cfg.max_kpts
+        kp = np.zeros((k, 2), np.int32); sc = np.zeros((k,), np.float32); n = C.c_int32(0)
+        _chk(_lib.dv_dbg_nms_select(self._h, _ptr(s, C.c_float), h8, w8, _ptr(nms, C.c_float), _ptr(kp, C.c_int32),
+                                    _ptr(sc, C.c_float), C.byref(n)))
+        return nms, kp[:n.value], sc[:n.value]
+
+    def dbg_match_extract(self, L):
+        L = _f32(L); m, n = L.shape
+        cap = max(1, min(m, n))
+        ma = np.zeros((cap, 2), np.int32); ms = np.zeros((cap,), np.float32); ko = C.c_int32(0)
+        _chk(_lib.dv_dbg_match_extract(self._h, _ptr(L, C.c_float), m, n, _ptr(ma, C.c_int32), _ptr(ms, C.c_float),
+                                       C.byref(ko)))
+        return ma[:ko.value], ms[:ko.value]
+
+    def dbg_read(self, name: str) -> np.ndarray:
+        cnt = C.c_int64(0)
+        _chk(_lib.dv_dbg_read(self._h, name.encode(), None, C.c_int64(0), C.byref(cnt)))
+        out = np.zeros((cnt.value,), np.float32)
+        _chk(_lib.dv_dbg_read(self._h, name.encode(), _ptr(out, C.c_float), C.c_int64(cnt.value), C.byref(cnt)))
+        return out

@@ -1,0 +1,283 @@
+// C-ABI implementation: engine lifetime, per-keyframe and batched entry points, measurement hooks.
+// The heavy lifting lives in sp.cu / mix.cu / lg.cu / knn.cu / gemm_umma.cu.
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+
+namespace dv {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* get_error() { return g_err.c_str(); }
+
+static int drain_stats(Engine* e) {
+  for (auto& p : e->pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(p.b);
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    e->stage_ms[p.stage] += ms;
+    e->ev_pool.push_back(p.a);
+    e->ev_pool.push_back(p.b);
+  }
+  e->pending.clear();
+  return DV_OK;
+}
+
+}  // namespace dv
+
+using namespace dv;
+
+#define DV_CHECK_ENGINE(e) do { if (!(e)) { dv::set_error("null engine"); return DV_ERR_INVALID; } } while (0)
+
+extern "C" {
+
+void dv_config_default(dv_config* c) {
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(dv_config);
+  c->device = 0;
+  c->height = 480; c->width = 752;
+  c->max_batch = 1;
+  c->max_kpts = 512; c->nms_radius = 4; c->det_thresh = 0.0005f; c->border = 4;
+  c->max_vio = 256;
+  c->knn_k = 3; c->exclude_recent = 50;
+  c->lg_filter_thresh = 0.1f; c->lg_max_kpts = 1024;
+  c->bank_capacity = 65536;
+  c->store_capacity = 64;
+  c->world_size = 1; c->rank = 0;
+  c->weights_path = nullptr;
+}
+
+const char* dv_last_error(void) { return dv::get_error(); }
+const char* dv_version(void) { return "d_vins_b200 0.1 (sm_100a)"; }
+
+dv_status dv_create(const dv_config* cfg, dv_engine** out) {
+  if (!cfg || !out || cfg->struct_size != (int32_t)sizeof(dv_config)) {
+    set_error("dv_create: null argument or dv_config size mismatch");
+    return DV_ERR_INVALID;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    cudaGetLastError();
+    set_error("dv_create: no CUDA device visible - this engine has no CPU fallback");
+    return DV_ERR_NOGPU;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { set_error("dv_create: bad device ordinal"); return DV_ERR_INVALID; }
+  cudaDeviceProp prop;
+  DV_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error(std::string("dv_create: device is not Blackwell sm_100 (") + prop.name + "); kernels are sm_100a-only");
+    return DV_ERR_NOGPU;
+  }
+  if (cfg->height < 64 || cfg->width < 64 || cfg->max_batch < 1 || cfg->max_kpts < 1 || cfg->max_kpts > 1024 ||
+      cfg->max_vio < 1 || cfg->max_vio > 512 || cfg->lg_max_kpts < 16 || cfg->lg_max_kpts > 2048 ||
+      cfg->knn_k < 1 || cfg->knn_k > 8 || cfg->nms_radius != 4 || cfg->world_size < 1 || cfg->rank < 0 ||
+      cfg->rank >= cfg->world_size || cfg->bank_capacity < 1 || cfg->store_capacity < 1) {
+    set_error("dv_create: configuration out of the supported range");
+    return DV_ERR_UNSUPPORTED;
+  }
+  DV_CUDA_OK(cudaSetDevice(cfg->device));
+  Engine* e = new Engine();
+  e->cfg = *cfg;
+  if (cfg->weights_path) { e->weights_path = cfg->weights_path; e->cfg.weights_path = e->weights_path.c_str(); }
+  e->B = cfg->max_batch; e->H = cfg->height; e->W = cfg->width;
+  e->h8 = e->H / 8; e->w8 = e->W / 8;
+  auto fail = [&](int rc) { dv_destroy(reinterpret_cast<dv_engine*>(e)); return (dv_status)rc; };
+  if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(DV_ERR_CUDA); }
+  cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
+  int rc = gemm_init();
+  if (rc) return fail(rc);
+  size_t img_bytes = (size_t)e->B * e->H * e->W * 3;
+  if ((rc = e->alloc(&e->d_img, img_bytes))) return fail(rc);
+  if ((rc = e->alloc_pinned(&e->h_img, img_bytes))) return fail(rc);
+  if (!e->weights_path.empty()) {
+    if ((rc = load_weight_file(e->weights_path.c_str(), &e->weights))) return fail(rc);
+    if ((rc = sp_init(e))) return fail(rc);
+    if ((rc = mix_init(e))) return fail(rc);
+    if ((rc = lg_init(e))) return fail(rc);
+  }
+  if ((rc = bank_init(e))) return fail(rc);
+  if ((rc = store_init(e))) return fail(rc);
+  if (cudaStreamSynchronize(e->st) != cudaSuccess) { set_error("engine init: device error"); return fail(DV_ERR_CUDA); }
+  e->weights.clear();   // host copies no longer needed
+  *out = reinterpret_cast<dv_engine*>(e);
+  return DV_OK;
+}
+
+void dv_destroy(dv_engine* h) {
+  if (!h) return;
+  Engine* e = reinterpret_cast<Engine*>(h);
+  cudaSetDevice(e->cfg.device);
+  if (e->st) cudaStreamSynchronize(e->st);
+  comm_free(e);
+  sp_free(e); mix_free(e); lg_free(e); bank_free(e); store_free(e);
+  for (void* p : e->allocs) cudaFree(p);
+  for (void* p : e->pinned) cudaFreeHost(p);
+  for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+  if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+  if (e->st) cudaStreamDestroy(e->st);
+  cudaGetLastError();
+  delete e;
+}
+
+// ------------------------------------------------------------------------------------------ measurement
+dv_status dv_timer_start(dv_engine* h) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  DV_CUDA_OK(cudaEventRecord(e->ev_t0, e->st));
+  return DV_OK;
+}
+dv_status dv_timer_stop(dv_engine* h, float* ms) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  DV_CUDA_OK(cudaEventRecord(e->ev_t1, e->st));
+  DV_CUDA_OK(cudaEventSynchronize(e->ev_t1));
+  float t = 0.f;
+  DV_CUDA_OK(cudaEventElapsedTime(&t, e->ev_t0, e->ev_t1));
+  if (ms) *ms = t;
+  return DV_OK;
+}
+dv_status dv_sync(dv_engine* h) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  return DV_OK;
+}
+dv_status dv_stats_enable(dv_engine* h, int32_t on) {
+  DV_CHECK_ENGINE(h);
+  reinterpret_cast<Engine*>(h)->stats_on = on != 0;
+  return DV_OK;
+}
+dv_status dv_stats_reset(dv_engine* h) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  drain_stats(e);
+  for (double& v : e->stage_ms) v = 0;
+  e->launches = 0;
+  return DV_OK;
+}
+dv_status dv_stats_read(dv_engine* h, double* stage_ms6, int64_t* launches) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  drain_stats(e);
+  if (stage_ms6) for (int i = 0; i < ST_COUNT; ++i) stage_ms6[i] = e->stage_ms[i];
+  if (launches) *launches = e->launches;
+  return DV_OK;
+}
+
+// ------------------------------------------------------------------------------------------ stage-level debug
+dv_status dv_dbg_gemm(dv_engine* h, const float* A, const float* Bm, const float* bias, int32_t M, int32_t N, int32_t K,
+                      int32_t relu, float* D) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!A || !Bm || !D || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 4)) {
+    set_error("dv_dbg_gemm: need K % 8 == 0, N % 4 == 0");
+    return DV_ERR_INVALID;
+  }
+  float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr, *dbias = nullptr;
+  __half *dA = nullptr, *dB = nullptr;
+  DV_CUDA_OK(cudaMalloc(&dA32, (size_t)M * K * 4));
+  DV_CUDA_OK(cudaMalloc(&dB32, (size_t)N * K * 4));
+  DV_CUDA_OK(cudaMalloc(&dA, (size_t)M * K * 2));
+  DV_CUDA_OK(cudaMalloc(&dB, (size_t)N * K * 2));
+  DV_CUDA_OK(cudaMalloc(&dD, (size_t)M * N * 4));
+  DV_CUDA_OK(cudaMemcpyAsync(dA32, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dB32, Bm, (size_t)N * K * 4, cudaMemcpyHostToDevice, e->st));
+  if (bias) {
+    DV_CUDA_OK(cudaMalloc(&dbias, (size_t)N * 4));
+    DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice, e->st));
+  }
+  f32_to_f16(dA32, dA, (int64_t)M * K, e->st);
+  f32_to_f16(dB32, dB, (int64_t)N * K, e->st);
+  EpiParams ep;
+  ep.out32 = dD; ep.ld32 = N; ep.bias = dbias; ep.relu = relu;
+  GemmPlan pl;
+  int rc = plan_gemm(&pl, dA, K, M, dB, K, N, K, ep);
+  if (!rc) rc = launch_gemm(pl, M, e->st);
+  if (!rc) {
+    cudaError_t ce = cudaMemcpyAsync(D, dD, (size_t)M * N * 4, cudaMemcpyDeviceToHost, e->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    if (ce != cudaSuccess) { set_error(std::string("dv_dbg_gemm: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
+  }
+  cudaFree(dA32); cudaFree(dB32); cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dbias);
+  return (dv_status)rc;
+}
+
+dv_status dv_dbg_conv3x3(dv_engine* h, const float* x, const float* wgt, const float* bias, int32_t n, int32_t hh,
+                         int32_t ww, int32_t cin, int32_t cout, int32_t relu, int32_t pool, float* y) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!x || !wgt || !y || n <= 0 || hh <= 0 || ww <= 0 || (cin % 64) || (cout % 8)) {
+    set_error("dv_dbg_conv3x3: need cin % 64 == 0, cout % 8 == 0");
+    return DV_ERR_INVALID;
+  }
+  const size_t nx = (size_t)n * hh * ww * cin;
+  const int ho = pool ? hh / 2 : hh, wo = pool ? ww / 2 : ww;
+  const size_t ny = (size_t)n * ho * wo * cout;
+  // repack torch [cout,cin,3,3] -> [cout, (r*3+s)*cin + c]
+  std::vector<float> wr((size_t)cout * 9 * cin);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * cin + c] = wgt[((size_t)o * cin + c) * 9 + t];
+  float *dx32 = nullptr, *dw32 = nullptr, *dy32 = nullptr, *dbias = nullptr;
+  __half *dx = nullptr, *dw = nullptr, *dy = nullptr;
+  DV_CUDA_OK(cudaMalloc(&dx32, nx * 4)); DV_CUDA_OK(cudaMalloc(&dx, nx * 2));
+  DV_CUDA_OK(cudaMalloc(&dw32, wr.size() * 4)); DV_CUDA_OK(cudaMalloc(&dw, wr.size() * 2));
+  DV_CUDA_OK(cudaMalloc(&dy, ny * 2)); DV_CUDA_OK(cudaMalloc(&dy32, ny * 4));
+  DV_CUDA_OK(cudaMemsetAsync(dy, 0, ny * 2, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dx32, x, nx * 4, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dw32, wr.data(), wr.size() * 4, cudaMemcpyHostToDevice, e->st));
+  if (bias) {
+    DV_CUDA_OK(cudaMalloc(&dbias, (size_t)cout * 4));
+    DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)cout * 4, cudaMemcpyHostToDevice, e->st));
+  }
+  f32_to_f16(dx32, dx, (int64_t)nx, e->st);
+  f32_to_f16(dw32, dw, (int64_t)wr.size(), e->st);
+  EpiParams ep;
+  ep.out16 = dy; ep.ld16 = cout; ep.bias = dbias; ep.relu = relu; ep.pool = pool;
+  GemmPlan pl;
+  int rc = plan_conv3x3(&pl, dx, n, hh, ww, cin, dw, cout, ep);
+  if (!rc) rc = launch_gemm(pl, n, e->st);
+  if (!rc) {
+    f16_to_f32(dy, dy32, (int64_t)ny, e->st);
+    cudaError_t ce = cudaMemcpyAsync(y, dy32, ny * 4, cudaMemcpyDeviceToHost, e->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    if (ce != cudaSuccess) { set_error(std::string("dv_dbg_conv3x3: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
+  }
+  cudaFree(dx32); cudaFree(dx); cudaFree(dw32); cudaFree(dw); cudaFree(dy); cudaFree(dy32); cudaFree(dbias);
+  return (dv_status)rc;
+}
+
+dv_status dv_dbg_read(dv_engine* h, const char* name, float* dst, int64_t capacity, int64_t* count) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  auto it = e->dbg.find(name ? name : "");
+  if (it == e->dbg.end()) { set_error(std::string("dv_dbg_read: unknown tensor ") + (name ? name : "(null)")); return DV_ERR_INVALID; }
+  const Engine::Dbg& d = it->second;
+  if (count) *count = d.n;
+  if (!dst) return DV_OK;
+  if (capacity < d.n) { set_error("dv_dbg_read: capacity too small"); return DV_ERR_CAPACITY; }
+  if (d.dtype == 0 || d.dtype == 2) {
+    DV_CUDA_OK(cudaMemcpyAsync(dst, d.p, (size_t)d.n * 4, cudaMemcpyDeviceToHost, e->st));
+  } else {
+    float* tmp = nullptr;
+    DV_CUDA_OK(cudaMalloc(&tmp, (size_t)d.n * 4));
+    f16_to_f32(reinterpret_cast<const __half*>(d.p), tmp, d.n, e->st);
+    cudaError_t ce = cudaMemcpyAsync(dst, tmp, (size_t)d.n * 4, cudaMemcpyDeviceToHost, e->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    cudaFree(tmp);
+    if (ce != cudaSuccess) { set_error(std::string("dv_dbg_read: ") + cudaGetErrorString(ce)); return DV_ERR_CUDA; }
+  }
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  return DV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// Internal engine state (not part of the C ABI).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dvins_perception.h"
+#include "common.cuh"
+#include "gemm.h"
+
+namespace dv {
+
+struct HostTensor {
+  std::vector<int> dims;
+  std::vector<float> data;
+  int64_t numel() const { int64_t n = 1; for (int d : dims) n *= d; return n; }
+};
+using WeightMap = std::map<std::string, HostTensor>;
+int load_weight_file(const char* path, WeightMap* out);   // weights.cpp
+
+enum Stage { ST_SP_CONV = 0, ST_SP_POST = 1, ST_MIX = 2, ST_KNN = 3, ST_LG = 4, ST_COPY = 5, ST_COUNT = 6 };
+
+struct SpNet;   // sp.cu
+struct MixNet;  // mix.cu
+struct LgNet;   // lg.cu
+struct Bank;    // knn.cu
+struct Store;   // engine.cpp (device-resident keyframe features)
+struct Comm;    // comm.cpp
+
+struct Engine {
+  dv_config cfg{};
+  std::string weights_path;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  int B = 1, H = 0, W = 0;
+  int h8 = 0, w8 = 0;          // encoder output grid = floor(H/8), floor(W/8)
+  WeightMap weights;
+  std::vector<void*> allocs;   // every device allocation, freed in dv_destroy
+  std::vector<void*> pinned;
+
+  // raw frames of the current batch
+  uint8_t* d_img = nullptr;    // [B, H, W, ch] u8 as uploaded
+  uint8_t* h_img = nullptr;    // pinned staging
+  int img_ch = 1;
+  int cur_b = 0;               // frames in the current batch
+  bool enc_done = false, det_done = false, mix_done = false;
+
+  SpNet* sp = nullptr;
+  MixNet* mix = nullptr;
+  LgNet* lg = nullptr;
+  Bank* bank = nullptr;
+  Store* store = nullptr;
+  Comm* comm = nullptr;
+
+  // stats
+  bool stats_on = false;
+  double stage_ms[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+  int64_t launches = 0;
+  struct Pending { int stage; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> ev_pool;
+
+  // debug tensors by name: device pointer + element count + dtype (0 f32, 1 f16, 2 i32)
+  struct Dbg { const void* p; int64_t n; int dtype; };
+  std::map<std::string, Dbg> dbg;
+
+  template <class T> int alloc(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e)); return DV_ERR_CUDA; }
+    cudaMemsetAsync(q, 0, count * sizeof(T) + 256, st);
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return DV_OK;
+  }
+  template <class T> int alloc_pinned(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMallocHost(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) { set_error(std::string("cudaMallocHost failed: ") + cudaGetErrorString(e)); return DV_ERR_CUDA; }
+    pinned.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return DV_OK;
+  }
+  const HostTensor* weight(const std::string& name) const {
+    auto it = weights.find(name);
+    return it == weights.end() ? nullptr : &it->second;
+  }
+  int upload_f16(const std::vector<float>& v, __half** out);
+  int upload_f32(const std::vector<float>& v, float** out);
+};
+
+// stage timing scope (no-op unless stats are enabled)
+struct StageScope {
+  Engine* e; int stage; cudaEvent_t a = nullptr, b = nullptr;
+  StageScope(Engine* e_, int s);
+  ~StageScope();
+};
+#define DV_LAUNCHED(e, n) ((e)->launches += (n))
+#define DV_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+// helper kernels (util.cu)
+void f32_to_f16(const float* src, __half* dst, int64_t n, cudaStream_t st);
+void f16_to_f32(const __half* src, float* dst, int64_t n, cudaStream_t st);
+
+// subsystem entry points --------------------------------------------------------------------------
+int sp_init(Engine* e);                       // sp.cu
+void sp_free(Engine* e);
+int sp_run_encoder(Engine* e, int b);         // gray -> conv1a .. heads (logits + dense descriptor map)
+int sp_run_detect(Engine* e, int b);          // softmax/d2s, NMS, select, sample -> device results
+int sp_run_describe(Engine* e, int b, const float* d_kpts, const int* d_n, int cap, float* d_desc);
+int sp_nms_select_dbg(Engine* e, const float* h_smap, int h8, int w8, float* h_nms, int32_t* kp, float* sc, int32_t* n);
+
+int mix_init(Engine* e);                      // mix.cu
+void mix_free(Engine* e);
+int mix_run(Engine* e, int b);                // -> e->mix global descriptors [b,512] on device
+
+int lg_init(Engine* e);                       // lg.cu
+void lg_free(Engine* e);
+
+int bank_init(Engine* e);                     // knn.cu
+void bank_free(Engine* e);
+
+int store_init(Engine* e);                    // store.cu
+void store_free(Engine* e);
+void comm_free(Engine* e);                    // comm.cpp
+
+}  // namespace dv

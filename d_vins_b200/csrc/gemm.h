@@ -1,0 +1,49 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution: host-side plan + launch API.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dv {
+
+// Fused epilogue, applied per accumulator row (= output pixel / token) in this order:
+//   v = acc + bias[col]; v += res16 / res32 (optional); relu (optional); 2x2 max-pool (conv only, optional);
+//   store fp16 (out16) and/or fp32 (out32).
+struct EpiParams {
+  __half* out16 = nullptr; int ld16 = 0;
+  float* out32 = nullptr; int ld32 = 0;
+  const float* bias = nullptr;
+  const __half* res16 = nullptr; int ldr16 = 0;
+  const float* res32 = nullptr; int ldr32 = 0;
+  int relu = 0;
+  int pool = 0;
+};
+
+struct GemmParams {
+  int M, N, K;          // M rows actually computed (set at launch), N output columns, K reduction length
+  int num_kb;           // K blocks of 64
+  int n_tiles;
+  int conv;             // 0: plain row-major A; 1: 3x3 pad-1 conv over NHWC A
+  int H, W, cin, cin_blocks, tw_log2, tiles_w, tiles_h;
+  EpiParams epi;
+};
+
+struct GemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmParams p;
+  int bn = 0;           // 64 or 128
+  int rows_cap = 0;     // plain: max M; conv: max images
+};
+
+// A [M_cap, K] fp16 row-major (row pitch lda elements), B = weights [N, K] fp16 row-major (pitch ldb).
+int plan_gemm(GemmPlan* pl, const __half* A, int lda, int M_cap, const __half* B, int ldb, int N, int K,
+              const EpiParams& epi, int bn = 0);
+// x NHWC [n_cap, H, W, cin] fp16 (cin % 64 == 0), w [cout, 9*cin] fp16 with k = (r*3+s)*cin + c.
+int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin, const __half* w, int cout,
+                 const EpiParams& epi);
+// rows = M (plain) or number of images (conv).
+int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st);
+int gemm_init();      // resolves cuTensorMapEncodeTiled, sets kernel attributes
+
+}  // namespace dv

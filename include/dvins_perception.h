@@ -1,0 +1,179 @@
+/*
+ * dvins_perception.h - C ABI of the B200-native loop-closure perception engine.
+ *
+ * Drop-in boundary for D_VINS' loop_fusion deep-perception facade (upstream paths relative to
+ * kajo-kurisu/D_VINS):
+ *   Estimator_net::Estimator  loop_fusion/src/deep_net/deep_net.h:141-171   (sp_extractor x2, lg_matcher)
+ *   MixVPR_net::MixVPR        loop_fusion/src/deep_net/deep_net.h:117-135   (mix_extractor)
+ *   KeyFrame::sort_vec_faiss  loop_fusion/src/keyframe.cpp:262-346          (faiss IndexFlatIP kNN)
+ * Plain C: opaque handle, POD arguments, caller-allocated outputs, no torch / OpenCV / STL types.
+ * Every entry point returns dv_status (0 = OK); the failing thread's message is in dv_last_error().
+ * Calls on ONE engine are serialised by contract (the reference calls everything from its single
+ * `process` thread, pose_graph_node.cpp:264-397); independent engines are fully concurrent.
+ * There is NO CPU fallback: dv_create fails with DV_ERR_NOGPU when no sm_100 device is visible.
+ *
+ * Precondition carried over from every shipped D_VINS config: network input size == image size
+ * (width_adj == image_width, height_adj == image_height); other sizes -> DV_ERR_UNSUPPORTED.
+ */
+#ifndef DVINS_PERCEPTION_H_
+#define DVINS_PERCEPTION_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DV_DESC_DIM 256        /* SuperPoint local descriptor width   (export/superpoint.py:108) */
+#define DV_GLOBAL_DIM 512      /* MixVPR global descriptor width      (keyframe.cpp:264)          */
+#define DV_MIX_HW 320          /* MixVPR network input side           (deep_net.cpp:1273)         */
+
+typedef struct dv_engine dv_engine;
+
+typedef enum dv_status {
+  DV_OK = 0,
+  DV_ERR_INVALID = 1,      /* bad argument / shape                                           */
+  DV_ERR_CUDA = 2,         /* CUDA runtime / driver failure (sticky)                         */
+  DV_ERR_UNSUPPORTED = 3,  /* configuration outside the precondition                         */
+  DV_ERR_WEIGHTS = 4,      /* weight file missing / malformed / tensor missing               */
+  DV_ERR_CAPACITY = 5,     /* bank / feature store / batch capacity exceeded                 */
+  DV_ERR_COMM = 6,         /* NCCL failure                                                   */
+  DV_ERR_NOGPU = 7         /* no Blackwell (sm_100) device: the engine refuses to run on CPU */
+} dv_status;
+
+/* Replaces the reference's compile-time #defines (deep_net.h:33-51), YAML keys (pose_graph_node.cpp:445-500)
+ * and export-time constants (export/superpoint.py:110-116; keyframe.cpp:264,274,294). */
+typedef struct dv_config {
+  int32_t struct_size;       /* = sizeof(dv_config), ABI guard                                   */
+  int32_t device;            /* CUDA device ordinal                                              */
+  int32_t height, width;     /* frame size == network size, e.g. 480x752 (euroc yaml:13-14)       */
+  int32_t max_batch;         /* frames (and LightGlue pairs) per batched call, >= 1              */
+  int32_t max_kpts;          /* SuperPoint top-k, 512                                            */
+  int32_t nms_radius;        /* 4                                                                */
+  float det_thresh;          /* 0.0005                                                           */
+  int32_t border;            /* 4                                                                */
+  int32_t max_vio;           /* capacity for caller-supplied (VIO / window) points per frame, <=512 */
+  int32_t knn_k;             /* 3  (keyframe.cpp:294)                                            */
+  int32_t exclude_recent;    /* 50 (keyframe.cpp:274)                                            */
+  float lg_filter_thresh;    /* 0.1                                                              */
+  int32_t lg_max_kpts;       /* per-image LightGlue capacity, 1024 (README.md:180)               */
+  int64_t bank_capacity;     /* rows of the global-descriptor bank                               */
+  int32_t store_capacity;    /* keyframes whose local features stay device-resident (ring)       */
+  int32_t world_size, rank;  /* frame-sharded ranks (1,0 = single GPU)                           */
+  const char* weights_path;  /* DVWGT001 file: sp.*, lg.*, mix.* tensors (see oracle/weights.py) */
+} dv_config;
+
+void dv_config_default(dv_config* cfg);
+const char* dv_last_error(void);
+const char* dv_version(void);
+
+/* Factories single_init / creat_mix / creat_estimator (deep_net.cpp:1184-1203, :1445) load four TensorRT engines
+ * at static-init time and return unchecked null pointers on failure; here: one explicit, checked call. */
+dv_status dv_create(const dv_config* cfg, dv_engine** out);
+void dv_destroy(dv_engine* e);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-keyframe API (latency path; mirrors the reference call sites 1:1).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One H2D copy of the frame, shared by SP, SP_RE and MixVPR (the reference uploads it three times:
+ * deep_net.cpp:575, :748, :1294).  img: u8, `channels` 1 (gray) or 3 (BGR), row pitch `stride` bytes. */
+dv_status dv_frame_upload(dv_engine* e, const uint8_t* img, int32_t height, int32_t width, int32_t stride,
+                          int32_t channels);
+
+/* Estimator::sp_extractor(img)  deep_net.cpp:527-688.  Outputs (host, caller-allocated, capacity max_kpts):
+ * kpts_xy [n,2] int32 pixel (x,y); scores [n]; desc [n,256] unit rows; kpts_norm [n,2] (may be NULL). */
+dv_status dv_sp_detect(dv_engine* e, int32_t* kpts_xy, float* scores, float* desc, float* kpts_norm, int32_t* n);
+
+/* Estimator::sp_extractor(img, kpts)  deep_net.cpp:690-812 (SP "recover"): describe at the caller's float pixel
+ * keypoints.  Shares the encoder pass of the uploaded frame (the reference runs the encoder a 2nd time). */
+dv_status dv_sp_describe(dv_engine* e, const float* kpts_xy, int32_t n, float* desc);
+
+/* MixVPR::mix_extractor(img)  deep_net.cpp:1254-1323 -> 512-d unit vector. */
+dv_status dv_mix_describe(dv_engine* e, float* des512);
+
+/* KeyFrame::compute_mix_des_test's append (keyframe.cpp:353): bank row id returned in *row. */
+dv_status dv_bank_append(dv_engine* e, const float* des512, int64_t* row);
+dv_status dv_bank_size(dv_engine* e, int64_t* rows);
+/* KeyFrame::sort_vec_faiss  keyframe.cpp:262-346: exact inner-product top-k over bank rows [0, nb_limit).
+ * D [k] descending, I [k]; padded with (-inf, -1) when nb_limit < k (faiss convention). */
+dv_status dv_bank_search(dv_engine* e, const float* q512, int64_t nb_limit, int32_t k, float* D, int64_t* I);
+/* "next" row SURVEY §8(f)-3: flat f32 [rows,512] persistence replacing pose_graph.cpp:1042-1069 / :1156-1194. */
+dv_status dv_bank_export(dv_engine* e, float* dst, int64_t max_rows, int64_t* rows);
+dv_status dv_bank_import(dv_engine* e, const float* src, int64_t rows);
+
+/* Estimator::lg_matcher(kpts0,kpts1,desc0,desc1,h0,w0,h1,w1)  deep_net.cpp:814-1000.
+ * kpts in pixels; 10 <= m,n <= lg_max_kpts.  matches [K,2] int32 ascending in i0 (keyframe.cpp:623-654 relies on
+ * it), mscores [K]; mkpts0/mkpts1 [K,2] de-normalised matched keypoints (may be NULL; the caller only uses their
+ * count, keyframe.cpp:621-632).  Output capacity: min(m,n). */
+dv_status dv_lg_match(dv_engine* e, const float* kpts0, int32_t m, const float* kpts1, int32_t n, const float* desc0,
+                      const float* desc1, int32_t h0, int32_t w0, int32_t h1, int32_t w1, int32_t* matches,
+                      float* mscores, float* mkpts0, float* mkpts1, int32_t* k_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched keyframe-round API (throughput path): b frames per rank per round, features stay
+ * device-resident in a per-rank feature store keyed by global keyframe index.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* imgs: b gray frames, frame i at imgs + i*frame_stride, row pitch `stride`. */
+dv_status dv_batch_upload(dv_engine* e, int32_t b, const uint8_t* imgs, int64_t frame_stride, int32_t stride);
+/* SP + SP_RE + MixVPR for the b uploaded frames.  vio_xy [b, max_vio, 2] pixel coords, n_vio [b];
+ * frame_ids [b] global keyframe indices.  Local features (kpts = SP ++ VIO, desc = SP ++ SP_RE, the concatenation
+ * contract of keyframe.cpp:401-432) are written into the feature store slot frame_id % store_capacity. */
+dv_status dv_batch_extract(dv_engine* e, int32_t b, const float* vio_xy, const int32_t* n_vio,
+                           const int64_t* frame_ids);
+/* Append the b new global descriptors to the bank.  world_size > 1: ONE ncclAllGather of [b,512] per rank, landing
+ * rank-major in every rank's bank (row = round_base + rank*b + i).  first_row = row of this rank's frame 0. */
+dv_status dv_batch_commit(dv_engine* e, int32_t b, int64_t* first_row);
+/* kNN for the b query descriptors of this round; nb_limit [b] (keyframe.cpp:274-282: index>=50 ? index-49 : index+1). */
+dv_status dv_batch_search(dv_engine* e, int32_t b, const int64_t* nb_limit, float* D, int64_t* I);
+/* LightGlue for b pairs: query = frame query_ids[i]'s window points + SP_RE descriptors (kpts0/desc0 of
+ * keyframe.cpp:605-618), old = frame old_ids[i]'s full keypoint set.  Both must be resident in THIS rank's store.
+ * matches [b, max_vio, 2], mscores [b, max_vio], k_out [b]. */
+dv_status dv_batch_match(dv_engine* e, int32_t b, const int64_t* query_ids, const int64_t* old_ids, int32_t* matches,
+                         float* mscores, int32_t* k_out);
+/* Read one stored keyframe back (tests / persistence): kpts [n,2] f32, desc [n,256], n_sp = SuperPoint share. */
+dv_status dv_store_read(dv_engine* e, int64_t frame_id, float* kpts_xy, float* desc, int32_t* n_total, int32_t* n_sp);
+/* Results of the last dv_batch_extract for frame slot i (host copies). */
+dv_status dv_batch_read_global(dv_engine* e, int32_t i, float* des512);
+
+/* Multi-GPU plumbing: the host passes the 128-byte ncclUniqueId it broadcast over its own channel
+ * (torch.distributed in bench.py).  rank/world_size come from dv_config. */
+dv_status dv_comm_unique_id(void* id128);
+dv_status dv_comm_init(dv_engine* e, const void* id128);
+
+/* ------------------------------------------------------------------------------------------------
+ * Measurement hooks: CUDA events on the engine's own stream (torch.cuda.Event cannot see it).
+ * ---------------------------------------------------------------------------------------------- */
+dv_status dv_timer_start(dv_engine* e);
+dv_status dv_timer_stop(dv_engine* e, float* ms);      /* records, synchronises, returns elapsed */
+dv_status dv_sync(dv_engine* e);
+/* Per-stage accumulated device time (ms) and kernel-launch count since the last reset.
+ * stage: 0 sp_convs, 1 sp_post, 2 mixvpr, 3 knn, 4 lightglue, 5 copies. */
+dv_status dv_stats_reset(dv_engine* e);
+dv_status dv_stats_read(dv_engine* e, double* stage_ms6, int64_t* launches);
+dv_status dv_stats_enable(dv_engine* e, int32_t on);   /* stage timing costs event records; off by default */
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage-level entry points (parity tests address every kernel family in isolation through these).
+ * ---------------------------------------------------------------------------------------------- */
+/* D[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (relu?) : fp32 host in/out, fp16 operands, fp32 accumulate on tcgen05. */
+dv_status dv_dbg_gemm(dv_engine* e, const float* A, const float* B, const float* bias, int32_t M, int32_t N, int32_t K,
+                      int32_t relu, float* D);
+/* 3x3 pad-1 conv on NHWC fp16 via the implicit-GEMM tcgen05 kernel: x [n,h,w,cin], wgt [cout,cin,3,3] (torch
+ * layout), y [n,h',w',cout] with h' = pool ? h/2 : h. */
+dv_status dv_dbg_conv3x3(dv_engine* e, const float* x, const float* wgt, const float* bias, int32_t n, int32_t h,
+                         int32_t w, int32_t cin, int32_t cout, int32_t relu, int32_t pool, float* y);
+/* NMS + border + threshold + top-k on a caller-supplied f32 score map [h8,w8] (integer stage in isolation). */
+dv_status dv_dbg_nms_select(dv_engine* e, const float* score_map, int32_t h8, int32_t w8, float* nms_out,
+                            int32_t* kpts_xy, float* scores, int32_t* n);
+/* Match extraction on a caller-supplied log-assignment matrix L [m,n]. */
+dv_status dv_dbg_match_extract(dv_engine* e, const float* L, int32_t m, int32_t n, int32_t* matches, float* mscores,
+                               int32_t* k_out);
+/* Intermediate tensors of the last per-frame run, by name ("score_map", "logits", "conv1b", ...), as fp32. */
+dv_status dv_dbg_read(dv_engine* e, const char* name, float* dst, int64_t capacity, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVINS_PERCEPTION_H_ */

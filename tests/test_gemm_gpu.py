@@ -1,0 +1,51 @@
+"""tcgen05 GEMM / implicit-GEMM conv3x3 vs an fp32 reference of the same op (through the C ABI)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from d_vins_b200 import capi
+    e = capi.Engine(height=64, width=64)      # no weights: stage-level entry points only
+    yield e
+    e.close()
+
+
+def _q(a):      # operands are rounded to fp16 on the device; compare against the same rounding
+    return a.astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 128, 256), (300, 80, 256), (1000, 400, 400),
+                                   (5640, 256, 1152), (77, 768, 256), (4096, 64, 576)])
+def test_gemm(eng, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    D = eng.dbg_gemm(A, B, bias, relu=True)
+    ref = np.maximum(_q(A).astype(np.float64) @ _q(B).astype(np.float64).T + bias, 0)
+    err = np.abs(D - ref).max()
+    assert err < 2e-3, err     # fp32 accumulation of exactly-representable fp16 products: order-of-summation only
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,pool", [(1, 16, 16, 64, 64, False), (2, 24, 40, 64, 64, True),
+                                                 (1, 30, 47, 128, 128, False), (1, 60, 94, 128, 256, False),
+                                                 (2, 17, 23, 64, 128, True), (1, 120, 188, 64, 64, True)])
+def test_conv3x3(eng, n, h, w, cin, cout, pool):
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(h * w + cin)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (9 * cin))).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+    y = eng.dbg_conv3x3(x, wt, bias, relu=True, pool=pool)
+    xt = torch.from_numpy(_q(x)).permute(0, 3, 1, 2).double()
+    r = F.relu(F.conv2d(xt, torch.from_numpy(_q(wt)).double(), torch.from_numpy(bias).double(), padding=1))
+    if pool:
+        r = F.max_pool2d(r, 2, 2)
+    ref = r.permute(0, 2, 3, 1).numpy()
+    assert y.shape == ref.shape
+    err = np.abs(y - ref).max()
+    assert err < 4e-3, err     # output stored as fp16 (rel 2^-11 of values up to ~4)
