@@ -100,7 +100,7 @@ struct StageScope {
   ~StageScope();
 };
 #define DV_LAUNCHED(e, n) ((e)->launches += (n))
-#define DV_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+#define DV_TRY(expr) do { int _rc = (expr); if (_rc) return (dv_status)_rc; } while (0)
 
 // helper kernels (util.cu)
 void f32_to_f16(const float* src, __half* dst, int64_t n, cudaStream_t st);
@@ -112,6 +112,8 @@ void sp_free(Engine* e);
 int sp_run_encoder(Engine* e, int b);         // gray -> conv1a .. heads (logits + dense descriptor map)
 int sp_run_detect(Engine* e, int b);          // softmax/d2s, NMS, select, sample -> device results
 int sp_run_describe(Engine* e, int b, const float* d_kpts, const int* d_n, int cap, float* d_desc);
+void sp_device_results(Engine* e, int** kpts, float** kpts_f, float** scores, int** n, float** desc, float** re_kpts,
+                       int** re_n, float** re_desc);
 int sp_nms_select_dbg(Engine* e, const float* h_smap, int h8, int w8, float* h_nms, int32_t* kp, float* sc, int32_t* n);
 
 int mix_init(Engine* e);                      // mix.cu

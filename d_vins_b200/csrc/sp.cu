@@ -1,0 +1,586 @@
+// SuperPoint on B200: VGG encoder + detector/descriptor heads on tcgen05 implicit-GEMM tiles (gemm_umma.cu),
+// and the HBM-bound post-net as coalesced kernels: softmax-65 + depth-to-space, fused 3-round 9x9 NMS tile kernel,
+// border/threshold/candidate emission, radix-select top-k + bitonic sort, bilinear descriptor sampling + L2.
+// Semantics follow the reference's export/superpoint.py:52-224 and export/ultrapoint.py:101-127 (see oracle/).
+#include <algorithm>
+
+#include "engine.h"
+
+namespace dv {
+
+struct SpNet {
+  // weights
+  float *w1a = nullptr, *b1a = nullptr;                 // conv1a fp32 [64,9],[64]
+  __half* w[9] = {};                                    // 1b,2a,2b,3a,3b,4a,4b,PD(512),(unused)
+  float* bias[9] = {};
+  __half *wPb = nullptr, *wDb = nullptr;
+  float *bPb = nullptr, *bDb = nullptr;
+  // activations (NHWC fp16)
+  float* gray = nullptr;                                // [B,H,W] f32
+  __half *a1a = nullptr, *a1b = nullptr, *a2a = nullptr, *a2b = nullptr, *a3a = nullptr, *a3b = nullptr,
+         *a4a = nullptr, *a4b = nullptr, *aPD = nullptr;
+  float *logits = nullptr, *dmap = nullptr;             // [B*h8*w8, 80], [B*h8*w8, 256]
+  GemmPlan p1b, p2a, p2b, p3a, p3b, p4a, p4b, pPD, pPb, pDb;
+  // post
+  float *smap = nullptr, *nms = nullptr;                // [B,H8,W8]
+  unsigned long long* cand = nullptr;                   // [B, H8*W8]
+  int* cand_cnt = nullptr;                              // [B]
+  int* kpts = nullptr;                                  // [B,K,2] int32 (x,y)
+  float* kpts_f = nullptr;                              // [B,K,2] float (x,y)
+  float* scores = nullptr;                              // [B,K]
+  int* n_kpts = nullptr;                                // [B]
+  float* desc = nullptr;                                // [B,K,256]
+  // SP_RE
+  float* re_kpts = nullptr;                             // [B,max_vio,2]
+  int* re_n = nullptr;                                  // [B]
+  float* re_desc = nullptr;                             // [B,max_vio,256]
+  int H8 = 0, W8 = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ kernels
+// preprocess_kernel.cu:193-346 under the identity-affine precondition: u8 * (1/255.f); 3-ch: BGR->RGB, gray mix.
+__global__ void k_gray(const uint8_t* __restrict__ img, float* __restrict__ out, int64_t npix, int ch) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float a = 1.0f / 255.0f;
+  if (ch == 1) {
+    out[i] = __fmul_rn((float)img[i], a);
+  } else {
+    const float b = (float)img[i * 3 + 0], g = (float)img[i * 3 + 1], r = (float)img[i * 3 + 2];
+    const float c0 = __fmul_rn(r, a), c1 = __fmul_rn(g, a), c2 = __fmul_rn(b, a);
+    out[i] = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, c0), __fmul_rn(0.587f, c1)), __fmul_rn(0.114f, c2));
+  }
+}
+
+// conv1a: C_in = 1 is not an MMA shape -> CUDA cores.  8 threads per pixel, 8 output channels each: a warp writes
+// 4 pixels x 128 B = 512 contiguous bytes of the NHWC fp16 output.
+__global__ void __launch_bounds__(256) k_conv1a(const float* __restrict__ gray, const float* __restrict__ w,
+                                                const float* __restrict__ bias, __half* __restrict__ out, int H,
+                                                int W) {
+  __shared__ float tile[3][130];
+  const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 128;
+  const float* g = gray + (int64_t)b * H * W;
+  for (int i = threadIdx.x; i < 3 * 130; i += 256) {
+    const int r = i / 130, c = i - r * 130;
+    const int yy = y + r - 1, xx = x0 + c - 1;
+    tile[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? g[(int64_t)yy * W + xx] : 0.f;
+  }
+  const int cg = threadIdx.x & 7, px = threadIdx.x >> 3;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = bias[cg * 8 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = w[(cg * 8 + c) * 9 + t];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int xl = px + it * 32;
+    const int x = x0 + xl;
+    if (x >= W) continue;
+    float in[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) in[r * 3 + s] = tile[r][xl + s];
+    __align__(16) __half2 hv[4];
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      float a0 = br[c], a1 = br[c + 1];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) { a0 = fmaf(wr[c][t], in[t], a0); a1 = fmaf(wr[c + 1][t], in[t], a1); }
+      hv[c >> 1] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+    }
+    *reinterpret_cast<uint4*>(out + (((int64_t)b * H + y) * W + x) * 64 + cg * 8) = *reinterpret_cast<uint4*>(hv);
+  }
+}
+
+// softmax over 65 logits, drop the dustbin, scatter the 64 cell scores to the 8x8 pixel block
+// (export/superpoint.py:174-177).  One warp per cell.
+__global__ void k_softmax_d2s(const float* __restrict__ logits, int ld, float* __restrict__ smap, int ncells, int h8,
+                              int w8) {
+  const int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= ncells) return;
+  const float* l = logits + (int64_t)cell * ld;
+  const float v0 = l[lane], v1 = l[lane + 32], v2 = l[64];
+  float m = fmaxf(fmaxf(v0, v1), v2);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  const float e0 = expf(v0 - m), e1 = expf(v1 - m), e2 = expf(v2 - m);
+  float s = e0 + e1;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  s += e2;
+  const int b = cell / (h8 * w8);
+  const int rem = cell - b * h8 * w8;
+  const int cy = rem / w8, cx = rem - cy * w8;
+  const int W8 = w8 * 8;
+  float* o = smap + (int64_t)b * h8 * 8 * W8 + (int64_t)cy * 8 * W8 + cx * 8;
+  o[(lane >> 3) * W8 + (lane & 7)] = e0 / s;
+  o[((lane + 32) >> 3) * W8 + (lane & 7)] = e1 / s;
+}
+
+// simple_nms (export/superpoint.py:52-69), radius 4, two refinement rounds, fused into one tile kernel.
+// Dependency radius = 4 + 8 + 8 = 20, so each 64x32 output tile loads a 104x72 region.  Separable 9-tap max in
+// shared memory; pixels outside the image are -inf and never "maxima" (== torch's implicit -inf padding).
+#define NMS_TW 64
+#define NMS_TH 32
+#define NMS_HALO 20
+#define NMS_RW (NMS_TW + 2 * NMS_HALO)
+#define NMS_RH (NMS_TH + 2 * NMS_HALO)
+#define NMS_RN (NMS_RW * NMS_RH)
+
+__device__ __forceinline__ void maxpool9_inplace(float* T2, float* T1) {
+  // T1 = rowmax(T2); T2 = colmax(T1).  Out-of-region taps are skipped (region edge == -inf padding).
+  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+    const int y = i / NMS_RW, x = i - y * NMS_RW;
+    const int lo = max(x - 4, 0), hi = min(x + 4, NMS_RW - 1);
+    float m = T2[y * NMS_RW + lo];
+    for (int xx = lo + 1; xx <= hi; ++xx) m = fmaxf(m, T2[y * NMS_RW + xx]);
+    T1[i] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+    const int y = i / NMS_RW, x = i - y * NMS_RW;
+    const int lo = max(y - 4, 0), hi = min(y + 4, NMS_RH - 1);
+    float m = T1[lo * NMS_RW + x];
+    for (int yy = lo + 1; yy <= hi; ++yy) m = fmaxf(m, T1[yy * NMS_RW + x]);
+    T2[i] = m;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_nms_select(const float* __restrict__ smap, float* __restrict__ nms_out,
+                                                    unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
+                                                    int H8, int W8, int border, float thresh) {
+  extern __shared__ float sm[];
+  float* S = sm;
+  float* T1 = S + NMS_RN;
+  float* T2 = T1 + NMS_RN;
+  uint8_t* MM = reinterpret_cast<uint8_t*>(T2 + NMS_RN);
+  uint8_t* SUPP = MM + NMS_RN;
+  const int b = blockIdx.z;
+  const int gx0 = blockIdx.x * NMS_TW - NMS_HALO, gy0 = blockIdx.y * NMS_TH - NMS_HALO;
+  const float* src = smap + (int64_t)b * H8 * W8;
+  const float NEG = -INFINITY;
+  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+    const int y = i / NMS_RW, x = i - y * NMS_RW;
+    const int gy = gy0 + y, gx = gx0 + x;
+    const bool in = gy >= 0 && gy < H8 && gx >= 0 && gx < W8;
+    const float v = in ? src[(int64_t)gy * W8 + gx] : NEG;
+    S[i] = v;
+    T2[i] = v;
+  }
+  __syncthreads();
+  maxpool9_inplace(T2, T1);
+  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+    const float v = S[i];
+    MM[i] = (v != NEG) && (v == T2[i]);
+  }
+  __syncthreads();
+  for (int round = 0; round < 2; ++round) {
+    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) T2[i] = MM[i] ? 1.f : 0.f;
+    __syncthreads();
+    maxpool9_inplace(T2, T1);
+    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+      const bool sp = T2[i] > 0.f;
+      SUPP[i] = sp;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+      const float v = S[i];
+      T2[i] = (v == NEG) ? NEG : (SUPP[i] ? 0.f : v);
+    }
+    __syncthreads();
+    maxpool9_inplace(T2, T1);
+    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
+      const float v = S[i];
+      if (v != NEG) {
+        const float ss = SUPP[i] ? 0.f : v;
+        if (ss == T2[i] && !SUPP[i]) MM[i] = 1;
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < NMS_TW * NMS_TH; i += blockDim.x) {
+    const int ty = i / NMS_TW, tx = i - ty * NMS_TW;
+    const int gy = blockIdx.y * NMS_TH + ty, gx = blockIdx.x * NMS_TW + tx;
+    if (gy >= H8 || gx >= W8) continue;
+    const int ri = (ty + NMS_HALO) * NMS_RW + tx + NMS_HALO;
+    const float v = MM[ri] ? S[ri] : 0.f;
+    const int64_t lin = (int64_t)gy * W8 + gx;
+    if (nms_out) nms_out[(int64_t)b * H8 * W8 + lin] = v;
+    // export/superpoint.py:183-195: border -> -1, strict threshold
+    const bool inb = gy >= border && gy < H8 - border && gx >= border && gx < W8 - border;
+    if (inb && v > thresh) {
+      const int slot = atomicAdd(&cand_cnt[b], 1);
+      // key: score bits (positive floats order as unsigned) then ~index => descending key = score desc, index asc
+      cand[(int64_t)b * H8 * W8 + slot] =
+          ((unsigned long long)__float_as_uint(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)lin);
+    }
+  }
+}
+
+// top-k selection per frame: exact k-th key by 8-bit radix select, then bitonic sort of the <= 1024 survivors.
+// <= k candidates: all kept, in row-major order (export/superpoint.py:76-77 returns them unsorted).
+__global__ void __launch_bounds__(1024) k_topk(const unsigned long long* __restrict__ cand,
+                                               const int* __restrict__ cand_cnt, int cap, int K, int W8,
+                                               int* __restrict__ kpts, float* __restrict__ kpts_f,
+                                               float* __restrict__ scores, int* __restrict__ n_out) {
+  __shared__ unsigned long long sel[1024];
+  __shared__ int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_k, s_nsel;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(cand_cnt[b], cap);
+  const unsigned long long* c = cand + (int64_t)b * cap;
+  const bool all = n <= K;
+  int nsel;
+  if (all) {
+    nsel = n;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned long long k = c[i];
+      sel[i] = (k << 32) | (k >> 32);   // sort by ~index descending == index ascending
+    }
+    __syncthreads();
+  } else {
+    if (tid == 0) { s_prefix = 0ull; s_k = K; s_nsel = 0; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned long long k = c[i];
+        if (pass == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(int)((k >> shift) & 255ull)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int cum = 0, kk = s_k;
+        for (int d = 255; d >= 0; --d) {
+          if (cum + hist[d] >= kk) { s_k = kk - cum; s_prefix = (prefix << 8) | (unsigned long long)d; break; }
+          cum += hist[d];
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned long long T = s_prefix;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned long long k = c[i];
+      if (k >= T) { const int p = atomicAdd(&s_nsel, 1); if (p < 1024) sel[p] = k; }
+    }
+    __syncthreads();
+    nsel = min(s_nsel, K);
+  }
+  int P = 1;
+  while (P < nsel) P <<= 1;
+  for (int i = nsel + tid; i < P; i += blockDim.x) sel[i] = 0ull;
+  __syncthreads();
+  for (int k2 = 2; k2 <= P; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = sel[i], d = sel[ixj];
+          const bool desc = (i & k2) == 0;
+          if (desc ? (a < d) : (a > d)) { sel[i] = d; sel[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < nsel; i += blockDim.x) {
+    unsigned long long k = sel[i];
+    if (all) k = (k << 32) | (k >> 32);
+    const unsigned lin = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+    const float sc = __uint_as_float((unsigned)(k >> 32));
+    const int y = (int)(lin / (unsigned)W8), x = (int)(lin - (unsigned)y * (unsigned)W8);
+    kpts[((int64_t)b * K + i) * 2 + 0] = x;
+    kpts[((int64_t)b * K + i) * 2 + 1] = y;
+    kpts_f[((int64_t)b * K + i) * 2 + 0] = (float)x;
+    kpts_f[((int64_t)b * K + i) * 2 + 1] = (float)y;
+    scores[(int64_t)b * K + i] = sc;
+  }
+  if (tid == 0) n_out[b] = nsel;
+}
+
+// sample_descriptors (export/superpoint.py:83-98): per-pixel L2-normalised dense map, bilinear grid_sample with
+// align_corners=True and zero padding, L2-normalise again.  One warp per keypoint, 8 channels per lane.
+__global__ void k_sample_desc(const float* __restrict__ dmap, int h8, int w8, const float* __restrict__ kpts,
+                              const int* __restrict__ n_kpts, int cap, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int kp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (kp >= n_kpts[b]) return;
+  const float kx = kpts[((int64_t)b * cap + kp) * 2 + 0], ky = kpts[((int64_t)b * cap + kp) * 2 + 1];
+  // keypoints - s/2 + 0.5; / (w*s - s/2 - 0.5); *2 - 1; grid_sample unnormalise ((g+1)/2)*(size-1)
+  const float ux = __fdiv_rn(kx - 3.5f, (float)(w8 * 8) - 4.5f), uy = __fdiv_rn(ky - 3.5f, (float)(h8 * 8) - 4.5f);
+  const float gx = __fsub_rn(__fmul_rn(ux, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(uy, 2.f), 1.f);
+  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.f), 0.5f), (float)(w8 - 1));
+  const float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.f), 0.5f), (float)(h8 - 1));
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx, wy1 = iy - fy, wx0 = (fx + 1.f) - ix, wy0 = (fy + 1.f) - iy;
+  const float wgt[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};   // nw, ne, sw, se
+  const int cx[4] = {x0, x1, x0, x1}, cy[4] = {y0, y0, y1, y1};
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (cx[c] < 0 || cx[c] >= w8 || cy[c] < 0 || cy[c] >= h8) continue;   // warp-uniform
+    const float4* p =
+        reinterpret_cast<const float4*>(dmap + (((int64_t)b * h8 + cy[c]) * w8 + cx[c]) * 256 + lane * 8);
+    const float4 a = __ldg(p), d = __ldg(p + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, d.x, d.y, d.z, d.w};
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = wgt[c] / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], inv, acc[j]);
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ss += acc[j] * acc[j];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  float4* o = reinterpret_cast<float4*>(out + ((int64_t)b * cap + kp) * 256 + lane * 8);
+  o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+  o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int get_conv(Engine* e, const std::string& name, int cout, int cin, std::vector<float>* w_packed,
+                    std::vector<float>* b) {
+  const HostTensor* w = e->weight("sp." + name + ".weight");
+  const HostTensor* bb = e->weight("sp." + name + ".bias");
+  if (!w || !bb || w->dims.size() != 4 || w->dims[0] != cout || w->dims[1] != cin || w->dims[2] != 3 ||
+      w->dims[3] != 3 || bb->numel() != cout) {
+    set_error("SuperPoint weights: missing or mis-shaped tensor sp." + name);
+    return DV_ERR_WEIGHTS;
+  }
+  // torch [cout,cin,3,3] -> [cout, (r*3+s)*cin + c]  (K-major rows for the implicit GEMM)
+  w_packed->resize((size_t)cout * 9 * cin);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 9; ++t) (*w_packed)[((size_t)o * 9 + t) * cin + c] = w->data[((size_t)o * cin + c) * 9 + t];
+  *b = bb->data;
+  return DV_OK;
+}
+
+int sp_init(Engine* e) {
+  SpNet* s = new SpNet();
+  e->sp = s;
+  const int B = e->B, H = e->H, W = e->W, h8 = e->h8, w8 = e->w8;
+  const int H2 = H / 2, W2 = W / 2, H4 = H2 / 2, W4 = W2 / 2;
+  s->H8 = h8 * 8; s->W8 = w8 * 8;
+  // ---- weights
+  {
+    const HostTensor* w = e->weight("sp.conv1a.weight");
+    const HostTensor* b = e->weight("sp.conv1a.bias");
+    if (!w || !b || w->numel() != 64 * 9 || b->numel() != 64) { set_error("SuperPoint weights: sp.conv1a"); return DV_ERR_WEIGHTS; }
+    DV_TRY(e->upload_f32(w->data, &s->w1a));
+    DV_TRY(e->upload_f32(b->data, &s->b1a));
+  }
+  struct L { const char* name; int cin, cout; };
+  const L layers[7] = {{"conv1b", 64, 64}, {"conv2a", 64, 64}, {"conv2b", 64, 64}, {"conv3a", 64, 128},
+                       {"conv3b", 128, 128}, {"conv4a", 128, 128}, {"conv4b", 128, 128}};
+  for (int i = 0; i < 7; ++i) {
+    std::vector<float> wp, b;
+    DV_TRY(get_conv(e, layers[i].name, layers[i].cout, layers[i].cin, &wp, &b));
+    DV_TRY(e->upload_f16(wp, &s->w[i]));
+    DV_TRY(e->upload_f32(b, &s->bias[i]));
+  }
+  {  // convPa ++ convDa share their input: one N=512 implicit GEMM
+    std::vector<float> wp, bp, wd, bd;
+    DV_TRY(get_conv(e, "convPa", 256, 128, &wp, &bp));
+    DV_TRY(get_conv(e, "convDa", 256, 128, &wd, &bd));
+    wp.insert(wp.end(), wd.begin(), wd.end());
+    bp.insert(bp.end(), bd.begin(), bd.end());
+    DV_TRY(e->upload_f16(wp, &s->w[7]));
+    DV_TRY(e->upload_f32(bp, &s->bias[7]));
+  }
+  {
+    const HostTensor* w = e->weight("sp.convPb.weight");
+    const HostTensor* b = e->weight("sp.convPb.bias");
+    const HostTensor* wd = e->weight("sp.convDb.weight");
+    const HostTensor* bd = e->weight("sp.convDb.bias");
+    if (!w || !b || !wd || !bd || w->numel() != 65 * 256 || b->numel() != 65 || wd->numel() != 256 * 256 ||
+        bd->numel() != 256) { set_error("SuperPoint weights: sp.convPb / sp.convDb"); return DV_ERR_WEIGHTS; }
+    std::vector<float> wp(80 * 256, 0.f), bp(80, 0.f);       // N padded 65 -> 80 (zero rows)
+    std::copy(w->data.begin(), w->data.end(), wp.begin());
+    std::copy(b->data.begin(), b->data.end(), bp.begin());
+    DV_TRY(e->upload_f16(wp, &s->wPb));
+    DV_TRY(e->upload_f32(bp, &s->bPb));
+    DV_TRY(e->upload_f16(wd->data, &s->wDb));
+    DV_TRY(e->upload_f32(bd->data, &s->bDb));
+  }
+  // ---- activations
+  const size_t P1 = (size_t)B * H * W, P2 = (size_t)B * H2 * W2, P4 = (size_t)B * H4 * W4, P8 = (size_t)B * h8 * w8;
+  DV_TRY(e->alloc(&s->gray, P1));
+  DV_TRY(e->alloc(&s->a1a, P1 * 64));
+  DV_TRY(e->alloc(&s->a1b, P2 * 64));
+  DV_TRY(e->alloc(&s->a2a, P2 * 64));
+  DV_TRY(e->alloc(&s->a2b, P4 * 64));
+  DV_TRY(e->alloc(&s->a3a, P4 * 128));
+  DV_TRY(e->alloc(&s->a3b, P8 * 128));
+  DV_TRY(e->alloc(&s->a4a, P8 * 128));
+  DV_TRY(e->alloc(&s->a4b, P8 * 128));
+  DV_TRY(e->alloc(&s->aPD, P8 * 512));
+  DV_TRY(e->alloc(&s->logits, P8 * 80));
+  DV_TRY(e->alloc(&s->dmap, P8 * 256));
+  const size_t PS = (size_t)B * s->H8 * s->W8;
+  const int K = e->cfg.max_kpts, V = e->cfg.max_vio;
+  DV_TRY(e->alloc(&s->smap, PS));
+  DV_TRY(e->alloc(&s->nms, PS));
+  DV_TRY(e->alloc(&s->cand, PS));
+  DV_TRY(e->alloc(&s->cand_cnt, (size_t)B));
+  DV_TRY(e->alloc(&s->kpts, (size_t)B * K * 2));
+  DV_TRY(e->alloc(&s->kpts_f, (size_t)B * K * 2));
+  DV_TRY(e->alloc(&s->scores, (size_t)B * K));
+  DV_TRY(e->alloc(&s->n_kpts, (size_t)B));
+  DV_TRY(e->alloc(&s->desc, (size_t)B * K * 256));
+  DV_TRY(e->alloc(&s->re_kpts, (size_t)B * V * 2));
+  DV_TRY(e->alloc(&s->re_n, (size_t)B));
+  DV_TRY(e->alloc(&s->re_desc, (size_t)B * V * 256));
+  // ---- plans
+  auto ep16 = [](__half* out, int ld, const float* bias, int relu, int pool) {
+    EpiParams ep; ep.out16 = out; ep.ld16 = ld; ep.bias = bias; ep.relu = relu; ep.pool = pool; return ep;
+  };
+  DV_TRY(plan_conv3x3(&s->p1b, s->a1a, B, H, W, 64, s->w[0], 64, ep16(s->a1b, 64, s->bias[0], 1, 1)));
+  DV_TRY(plan_conv3x3(&s->p2a, s->a1b, B, H2, W2, 64, s->w[1], 64, ep16(s->a2a, 64, s->bias[1], 1, 0)));
+  DV_TRY(plan_conv3x3(&s->p2b, s->a2a, B, H2, W2, 64, s->w[2], 64, ep16(s->a2b, 64, s->bias[2], 1, 1)));
+  DV_TRY(plan_conv3x3(&s->p3a, s->a2b, B, H4, W4, 64, s->w[3], 128, ep16(s->a3a, 128, s->bias[3], 1, 0)));
+  DV_TRY(plan_conv3x3(&s->p3b, s->a3a, B, H4, W4, 128, s->w[4], 128, ep16(s->a3b, 128, s->bias[4], 1, 1)));
+  DV_TRY(plan_conv3x3(&s->p4a, s->a3b, B, h8, w8, 128, s->w[5], 128, ep16(s->a4a, 128, s->bias[5], 1, 0)));
+  DV_TRY(plan_conv3x3(&s->p4b, s->a4a, B, h8, w8, 128, s->w[6], 128, ep16(s->a4b, 128, s->bias[6], 1, 0)));
+  DV_TRY(plan_conv3x3(&s->pPD, s->a4b, B, h8, w8, 128, s->w[7], 512, ep16(s->aPD, 512, s->bias[7], 1, 0)));
+  {
+    EpiParams ep; ep.out32 = s->logits; ep.ld32 = 80; ep.bias = s->bPb;
+    DV_TRY(plan_gemm(&s->pPb, s->aPD, 512, (int)P8, s->wPb, 256, 80, 256, ep));
+    EpiParams ed; ed.out32 = s->dmap; ed.ld32 = 256; ed.bias = s->bDb;
+    DV_TRY(plan_gemm(&s->pDb, s->aPD + 256, 512, (int)P8, s->wDb, 256, 256, 256, ed));
+  }
+  DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  NMS_RN * (3 * 4 + 2)));
+  // debug views
+  e->dbg["gray"] = {s->gray, (int64_t)H * W, 0};
+  e->dbg["conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
+  e->dbg["conv1b_pool"] = {s->a1b, (int64_t)H2 * W2 * 64, 1};
+  e->dbg["conv2a"] = {s->a2a, (int64_t)H2 * W2 * 64, 1};
+  e->dbg["conv2b_pool"] = {s->a2b, (int64_t)H4 * W4 * 64, 1};
+  e->dbg["conv3a"] = {s->a3a, (int64_t)H4 * W4 * 128, 1};
+  e->dbg["conv3b_pool"] = {s->a3b, (int64_t)h8 * w8 * 128, 1};
+  e->dbg["conv4a"] = {s->a4a, (int64_t)h8 * w8 * 128, 1};
+  e->dbg["conv4b"] = {s->a4b, (int64_t)h8 * w8 * 128, 1};
+  e->dbg["convPD"] = {s->aPD, (int64_t)h8 * w8 * 512, 1};
+  e->dbg["logits"] = {s->logits, (int64_t)h8 * w8 * 80, 0};
+  e->dbg["dmap"] = {s->dmap, (int64_t)h8 * w8 * 256, 0};
+  e->dbg["score_map"] = {s->smap, (int64_t)s->H8 * s->W8, 0};
+  e->dbg["nms"] = {s->nms, (int64_t)s->H8 * s->W8, 0};
+  return DV_OK;
+}
+
+void sp_free(Engine* e) {
+  delete e->sp;
+  e->sp = nullptr;
+}
+
+int sp_run_encoder(Engine* e, int b) {
+  SpNet* s = e->sp;
+  if (!s) { set_error("SuperPoint not initialised (engine created without weights)"); return DV_ERR_INVALID; }
+  StageScope sc(e, ST_SP_CONV);
+  const int H = e->H, W = e->W;
+  const int64_t npix = (int64_t)b * H * W;
+  k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
+  k_conv1a<<<dim3(cdiv(W, 128), H, b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
+  DV_CUDA_OK(cudaGetLastError());
+  DV_TRY(launch_gemm(s->p1b, b, e->st));
+  DV_TRY(launch_gemm(s->p2a, b, e->st));
+  DV_TRY(launch_gemm(s->p2b, b, e->st));
+  DV_TRY(launch_gemm(s->p3a, b, e->st));
+  DV_TRY(launch_gemm(s->p3b, b, e->st));
+  DV_TRY(launch_gemm(s->p4a, b, e->st));
+  DV_TRY(launch_gemm(s->p4b, b, e->st));
+  DV_TRY(launch_gemm(s->pPD, b, e->st));
+  const int rows = b * e->h8 * e->w8;
+  DV_TRY(launch_gemm(s->pPb, rows, e->st));
+  DV_TRY(launch_gemm(s->pDb, rows, e->st));
+  DV_LAUNCHED(e, 12);
+  return DV_OK;
+}
+
+static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
+  SpNet* s = e->sp;
+  const int H8 = s->H8, W8 = s->W8, K = e->cfg.max_kpts;
+  DV_CUDA_OK(cudaMemsetAsync(s->cand_cnt, 0, sizeof(int) * b, e->st));
+  k_nms_select<<<dim3(cdiv(W8, NMS_TW), cdiv(H8, NMS_TH), b), 256, NMS_RN * (3 * 4 + 2), e->st>>>(
+      smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
+  k_topk<<<b, 1024, 0, e->st>>>(s->cand, s->cand_cnt, H8 * W8, K, W8, s->kpts, s->kpts_f, s->scores, s->n_kpts);
+  DV_CUDA_OK(cudaGetLastError());
+  DV_LAUNCHED(e, 2);
+  return DV_OK;
+}
+
+int sp_run_detect(Engine* e, int b) {
+  SpNet* s = e->sp;
+  StageScope sc(e, ST_SP_POST);
+  const int ncells = b * e->h8 * e->w8;
+  k_softmax_d2s<<<cdiv(ncells, 8), 256, 0, e->st>>>(s->logits, 80, s->smap, ncells, e->h8, e->w8);
+  DV_TRY(run_post(e, b, s->smap, s->nms));
+  const int K = e->cfg.max_kpts;
+  k_sample_desc<<<dim3(cdiv(K, 8), b), 256, 0, e->st>>>(s->dmap, e->h8, e->w8, s->kpts_f, s->n_kpts, K, s->desc);
+  DV_CUDA_OK(cudaGetLastError());
+  DV_LAUNCHED(e, 2);
+  return DV_OK;
+}
+
+int sp_run_describe(Engine* e, int b, const float* d_kpts, const int* d_n, int cap, float* d_desc) {
+  SpNet* s = e->sp;
+  StageScope sc(e, ST_SP_POST);
+  k_sample_desc<<<dim3(cdiv(cap, 8), b), 256, 0, e->st>>>(s->dmap, e->h8, e->w8, d_kpts, d_n, cap, d_desc);
+  DV_CUDA_OK(cudaGetLastError());
+  DV_LAUNCHED(e, 1);
+  return DV_OK;
+}
+
+// accessors used by engine.cpp / store.cu
+void sp_device_results(Engine* e, int** kpts, float** kpts_f, float** scores, int** n, float** desc, float** re_kpts,
+                       int** re_n, float** re_desc) {
+  SpNet* s = e->sp;
+  if (kpts) *kpts = s->kpts;
+  if (kpts_f) *kpts_f = s->kpts_f;
+  if (scores) *scores = s->scores;
+  if (n) *n = s->n_kpts;
+  if (desc) *desc = s->desc;
+  if (re_kpts) *re_kpts = s->re_kpts;
+  if (re_n) *re_n = s->re_n;
+  if (re_desc) *re_desc = s->re_desc;
+}
+
+int sp_nms_select_dbg(Engine* e, const float* h_smap, int h8x8, int w8x8, float* h_nms, int32_t* kp, float* sc,
+                      int32_t* n) {
+  SpNet* s = e->sp;
+  if (!s) { set_error("dv_dbg_nms_select needs an engine created with weights"); return DV_ERR_INVALID; }
+  if (h8x8 != s->H8 || w8x8 != s->W8) { set_error("dv_dbg_nms_select: score map must be [8*(H/8), 8*(W/8)]"); return DV_ERR_INVALID; }
+  const size_t np = (size_t)h8x8 * w8x8;
+  DV_CUDA_OK(cudaMemcpyAsync(s->smap, h_smap, np * 4, cudaMemcpyHostToDevice, e->st));
+  DV_TRY(run_post(e, 1, s->smap, s->nms));
+  int cnt = 0;
+  DV_CUDA_OK(cudaMemcpyAsync(&cnt, s->n_kpts, 4, cudaMemcpyDeviceToHost, e->st));
+  if (h_nms) DV_CUDA_OK(cudaMemcpyAsync(h_nms, s->nms, np * 4, cudaMemcpyDeviceToHost, e->st));
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(kp, s->kpts, (size_t)cnt * 8, cudaMemcpyDeviceToHost, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(sc, s->scores, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->st));
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  *n = cnt;
+  e->enc_done = e->det_done = false;
+  return DV_OK;
+}
+
+}  // namespace dv

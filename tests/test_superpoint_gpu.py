@@ -1,0 +1,127 @@
+"""SuperPoint / SP_RE parity: CUDA path (through the C ABI) vs the CPU oracle on identical seeded frames."""
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(weights_file):
+    from d_vins_b200 import capi
+    e = capi.Engine(height=480, width=752, weights_path=weights_file)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def frame_and_oracle(all_weights):
+    from oracle import superpoint as osp, synth, weights
+    img = synth.make_frame(480, 752, synth.BASE_SEED)
+    keep = {}
+    o = osp.superpoint(weights.sub(all_weights, "sp."), img, keep=keep)
+    return img, o, keep
+
+
+def test_nms_topk_bit_exact_on_identical_scores(eng, frame_and_oracle):
+    """Integer stage in isolation: same f32 score map in -> same NMS survivors, same keypoints, same order."""
+    _, o, _ = frame_and_oracle
+    nms, kp, sc = eng.dbg_nms_select(o["score_map"])
+    assert np.array_equal(nms, o["nms"])
+    assert np.array_equal(kp, o["kpts"])
+    assert np.array_equal(sc, o["scores"])
+
+
+def test_nms_topk_few_candidates_row_major(eng):
+    """<= k candidates stay in row-major order, unsorted (export/superpoint.py:76-77); plateaus all survive."""
+    from oracle import superpoint as osp
+    import torch
+    rng = np.random.default_rng(3)
+    s = np.zeros((480, 752), np.float32)
+    ys = rng.integers(10, 470, 200); xs = rng.integers(10, 740, 200)
+    s[ys, xs] = rng.uniform(0.01, 0.9, 200).astype(np.float32)
+    s[100:103, 200:203] = 0.5          # plateau: every pixel equals its window max
+    s[0:6, 0:6] = 0.7                  # inside the border: removed
+    nms_o = osp.simple_nms(torch.from_numpy(s))
+    kp_o, sc_o, _ = osp.select_keypoints(nms_o, 512)
+    nms, kp, sc = eng.dbg_nms_select(s)
+    assert np.array_equal(nms, nms_o.numpy())
+    assert np.array_equal(kp, kp_o.numpy().astype(np.int32))
+    assert np.array_equal(sc, sc_o.numpy())
+
+
+def test_encoder_activations(eng, frame_and_oracle):
+    img, o, keep = frame_and_oracle
+    eng.frame_upload(img)
+    eng.sp_detect()
+    for name, key in (("conv1a", "conv1a"), ("conv2a", "conv2a"), ("conv3a", "conv3a"), ("conv4a", "conv4a"),
+                      ("conv4b", "conv4b")):
+        ref = parity.nhwc(keep[key])
+        got = eng.dbg_read(name).reshape(ref.shape)
+        err = np.abs(got - ref).max()
+        assert err < 0.03 * max(1.0, np.abs(ref).max()), (name, err)
+    ref = parity.nhwc(keep["logits"])
+    got = eng.dbg_read("logits").reshape(60, 94, 80)[:, :, :65]
+    assert np.abs(got - ref).max() < 0.08, np.abs(got - ref).max()
+    sm = eng.dbg_read("score_map").reshape(480, 752)
+    assert np.abs(sm - o["score_map"]).max() < parity.SCORE_ATOL
+
+
+def test_superpoint_end_to_end(eng, frame_and_oracle):
+    img, o, _ = frame_and_oracle
+    eng.frame_upload(img)
+    r = eng.sp_detect()
+    assert len(r["kpts"]) == len(o["kpts"]) == 512
+    exact, missing, unexplained, rep = parity.check_keypoints(o, r)
+    print(rep)
+    assert missing == 0 and unexplained == 0, rep
+    assert exact >= 0.9 * len(o["kpts"]), rep
+    # floats on the common keypoints
+    oi = {(int(x), int(y)): i for i, (x, y) in enumerate(o["kpts"])}
+    pairs = [(oi[(int(x), int(y))], j) for j, (x, y) in enumerate(r["kpts"]) if (int(x), int(y)) in oi]
+    io, ig = np.array(pairs).T
+    assert np.abs(o["scores"][io] - r["scores"][ig]).max() < parity.SCORE_ATOL
+    cos = (o["desc"][io] * r["desc"][ig]).sum(1)
+    assert cos.min() > parity.DESC_COS_MIN, cos.min()
+    assert np.abs(o["desc"][io] - r["desc"][ig]).max() < parity.DESC_ATOL
+    assert np.allclose(np.linalg.norm(r["desc"], axis=1), 1.0, atol=1e-5)
+    # normalised keypoints: integer halves (deep_net.cpp:633-659)
+    from oracle import superpoint as osp
+    assert np.array_equal(r["kpts_norm"], osp.normalize_kpts(r["kpts"], 752, 480))
+    # scores sorted descending (top-k active)
+    assert np.all(np.diff(r["scores"]) <= 0)
+
+
+def test_sp_recover(eng, frame_and_oracle, all_weights):
+    from oracle import superpoint as osp, synth, weights
+    img, o, _ = frame_and_oracle
+    vio = synth.vio_points(150, 480, 752, synth.BASE_SEED + 3)
+    ref = osp.superpoint_recover(weights.sub(all_weights, "sp."), img, vio, feat=o["feat"])
+    eng.frame_upload(img)
+    got = eng.sp_describe(vio)
+    cos = (ref * got).sum(1)
+    assert cos.min() > parity.DESC_COS_MIN, cos.min()
+    assert np.abs(ref - got).max() < parity.DESC_ATOL
+
+
+def test_golden_fixture_matches_engine(eng):
+    """Committed golden vectors produced by the reference's own export/superpoint.py (tests/golden/make_golden.py)."""
+    import os
+    from oracle import synth
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sp_euroc.npz"))
+    img = synth.make_frame(480, 752, synth.BASE_SEED)
+    eng.frame_upload(img)
+    r = eng.sp_detect()
+    gs = {(int(x), int(y)) for x, y in g["kpts"]}
+    rs = {(int(x), int(y)) for x, y in r["kpts"]}
+    assert len(gs & rs) >= 0.9 * len(gs)
+    de = eng.sp_describe(g["vio"])
+    cos = (de[:48] * g["desc_r_head"]).sum(1)
+    assert cos.min() > parity.DESC_COS_MIN
+
+
+def test_rejects_wrong_size(eng):
+    from d_vins_b200 import capi
+    with pytest.raises(capi.DvError):
+        eng.frame_upload(np.zeros((100, 100), np.uint8))
