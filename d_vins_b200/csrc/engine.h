@@ -118,7 +118,8 @@ int sp_nms_select_dbg(Engine* e, const float* h_smap, int h8, int w8, float* h_n
 
 int mix_init(Engine* e);                      // mix.cu
 void mix_free(Engine* e);
-int mix_run(Engine* e, int b);                // -> e->mix global descriptors [b,512] on device
+int mix_run(Engine* e, int b);                // -> global descriptors [b,512] on device
+float* mix_gdesc(Engine* e);
 
 int lg_init(Engine* e);                       // lg.cu
 void lg_free(Engine* e);

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           if (g * 4 + 4 <= ncols) {
-            const float4 t = __ldg(rp + g);
+            const float4 t = rp[g];   // plain load: may alias out32 (in-place residual)
             v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
           }
       }

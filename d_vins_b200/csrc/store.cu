@@ -1,0 +1,243 @@
+// Device-resident keyframe feature store + the batched keyframe-round API (throughput path, SURVEY §8(e),(f)-1).
+// A keyframe's local features never leave the GPU between extraction and matching: kpts = SP ++ VIO points,
+// desc = SP descriptors ++ SP_RE descriptors - the concatenation contract of keyframe.cpp:401-432.
+#include <string.h>
+
+#include <algorithm>
+
+#include "engine.h"
+#include "lg.h"
+
+namespace dv {
+
+int comm_allgather(Engine* e, const float* send, float* recv, size_t count_per_rank);   // comm.cpp
+float* bank_rows(Engine* e);
+float* bank_query_buf(Engine* e);
+int64_t& bank_size_ref(Engine* e);
+int bank_search_device(Engine* e, int nq, const int64_t* nb_limit, int k, float* D_host, int64_t* I_host);
+
+struct Store {
+  int slots = 0, cap = 0;          // cap = max_kpts + max_vio rows per keyframe
+  float* kpts = nullptr;           // [slots, cap, 2]
+  float* desc = nullptr;           // [slots, cap, 256]
+  std::vector<int64_t> frame_id;   // host metadata
+  std::vector<int> n_sp, n_vio;
+  // batch staging
+  float* h_vio = nullptr; int* h_nvio = nullptr; int* h_nsp = nullptr; int* d_slot = nullptr; int* h_slot = nullptr;
+  std::vector<int64_t> cur_ids;
+  int cur_b = 0;
+};
+
+// one block per (frame, row chunk): rows [0,n_sp) from the SuperPoint outputs, rows [n_sp, n_sp+n_vio) from SP_RE
+__global__ void k_store_write(const float* __restrict__ sp_kpts, const float* __restrict__ sp_desc,
+                              const int* __restrict__ n_sp, int K, const float* __restrict__ re_kpts,
+                              const float* __restrict__ re_desc, const int* __restrict__ n_vio, int V,
+                              const int* __restrict__ slot, float* __restrict__ st_kpts, float* __restrict__ st_desc,
+                              int cap) {
+  const int f = blockIdx.y;
+  const int ns = n_sp[f], nv = n_vio[f];
+  const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
+  float* ok = st_kpts + (int64_t)slot[f] * cap * 2;
+  float* od = st_desc + (int64_t)slot[f] * cap * 256;
+  for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < ns + nv; r += gridDim.x * warps) {
+    const float* sk; const float* sd;
+    if (r < ns) { sk = sp_kpts + ((int64_t)f * K + r) * 2; sd = sp_desc + ((int64_t)f * K + r) * 256; }
+    else { sk = re_kpts + ((int64_t)f * V + (r - ns)) * 2; sd = re_desc + ((int64_t)f * V + (r - ns)) * 256; }
+    if (lane < 2) ok[r * 2 + lane] = sk[lane];
+    const float4* s4 = reinterpret_cast<const float4*>(sd);
+    float4* d4 = reinterpret_cast<float4*>(od + (int64_t)r * 256);
+    d4[lane] = s4[lane];
+    d4[lane + 32] = s4[lane + 32];
+  }
+}
+
+int store_init(Engine* e) {
+  Store* s = new Store();
+  e->store = s;
+  s->slots = e->cfg.store_capacity;
+  s->cap = e->cfg.max_kpts + e->cfg.max_vio;
+  s->frame_id.assign(s->slots, -1);
+  s->n_sp.assign(s->slots, 0);
+  s->n_vio.assign(s->slots, 0);
+  DV_TRY(e->alloc(&s->kpts, (size_t)s->slots * s->cap * 2));
+  DV_TRY(e->alloc(&s->desc, (size_t)s->slots * s->cap * 256));
+  DV_TRY(e->alloc_pinned(&s->h_vio, (size_t)e->B * e->cfg.max_vio * 2));
+  DV_TRY(e->alloc_pinned(&s->h_nvio, (size_t)e->B));
+  DV_TRY(e->alloc_pinned(&s->h_nsp, (size_t)e->B));
+  DV_TRY(e->alloc_pinned(&s->h_slot, (size_t)e->B));
+  DV_TRY(e->alloc(&s->d_slot, (size_t)e->B));
+  return DV_OK;
+}
+void store_free(Engine* e) { delete e->store; e->store = nullptr; }
+
+}  // namespace dv
+
+using namespace dv;
+#define DV_CHECK_ENGINE(e) do { if (!(e)) { dv::set_error("null engine"); return DV_ERR_INVALID; } } while (0)
+
+extern "C" {
+
+dv_status dv_batch_upload(dv_engine* h, int32_t b, const uint8_t* imgs, int64_t frame_stride, int32_t stride) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!imgs || b < 1 || b > e->B || stride < e->W || frame_stride < (int64_t)stride * e->H) { set_error("dv_batch_upload: bad arguments"); return DV_ERR_INVALID; }
+  StageScope sc(e, ST_COPY);
+  const size_t fb = (size_t)e->H * e->W;
+  if (stride == e->W && frame_stride == (int64_t)fb) {
+    // contiguous (typically already pinned by the caller): one async copy straight from the caller's buffer
+    DV_CUDA_OK(cudaMemcpyAsync(e->d_img, imgs, fb * b, cudaMemcpyHostToDevice, e->st));
+  } else {
+    DV_CUDA_OK(cudaMemcpy2DAsync(e->d_img, e->W, imgs, stride, e->W, (size_t)e->H, cudaMemcpyHostToDevice, e->st));
+    for (int i = 1; i < b; ++i)
+      DV_CUDA_OK(cudaMemcpy2DAsync(e->d_img + fb * i, e->W, imgs + frame_stride * i, stride, e->W, (size_t)e->H, cudaMemcpyHostToDevice, e->st));
+  }
+  e->img_ch = 1;
+  e->cur_b = b;
+  e->enc_done = e->det_done = e->mix_done = false;
+  return DV_OK;
+}
+
+dv_status dv_batch_extract(dv_engine* h, int32_t b, const float* vio_xy, const int32_t* n_vio, const int64_t* frame_ids) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  Store* s = e->store;
+  if (!e->sp || !e->mix) { set_error("dv_batch_extract: engine created without weights"); return DV_ERR_INVALID; }
+  if (b < 1 || b != e->cur_b || !vio_xy || !n_vio || !frame_ids) { set_error("dv_batch_extract: b must equal the uploaded batch"); return DV_ERR_INVALID; }
+  const int V = e->cfg.max_vio, K = e->cfg.max_kpts;
+  for (int i = 0; i < b; ++i) {
+    if (n_vio[i] < 0 || n_vio[i] > V || frame_ids[i] < 0) { set_error("dv_batch_extract: n_vio / frame id out of range"); return DV_ERR_INVALID; }
+    s->h_nvio[i] = n_vio[i];
+    s->h_slot[i] = (int)(frame_ids[i] % s->slots);
+  }
+  for (int i = 0; i < b; ++i)
+    for (int j = i + 1; j < b; ++j)
+      if (s->h_slot[i] == s->h_slot[j]) { set_error("dv_batch_extract: store_capacity too small for this batch"); return DV_ERR_CAPACITY; }
+  memcpy(s->h_vio, vio_xy, sizeof(float) * 2 * V * b);
+  float *d_rk, *d_rd, *d_kf, *d_de; int *d_rn, *d_n;
+  sp_device_results(e, nullptr, &d_kf, nullptr, &d_n, &d_de, &d_rk, &d_rn, &d_rd);
+  {
+    StageScope sc(e, ST_COPY);
+    DV_CUDA_OK(cudaMemcpyAsync(d_rk, s->h_vio, sizeof(float) * 2 * V * b, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(d_rn, s->h_nvio, sizeof(int) * b, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(s->d_slot, s->h_slot, sizeof(int) * b, cudaMemcpyHostToDevice, e->st));
+  }
+  DV_TRY(sp_run_encoder(e, b));
+  DV_TRY(sp_run_detect(e, b));
+  DV_TRY(sp_run_describe(e, b, d_rk, d_rn, V, d_rd));     // same encoder pass (the reference runs it twice)
+  DV_TRY(mix_run(e, b));
+  e->enc_done = e->det_done = e->mix_done = true;
+  {
+    StageScope sc(e, ST_SP_POST);
+    k_store_write<<<dim3(8, b), 256, 0, e->st>>>(d_kf, d_de, d_n, K, d_rk, d_rd, d_rn, V, s->d_slot, s->kpts, s->desc, s->cap);
+    DV_CUDA_OK(cudaGetLastError());
+    DV_LAUNCHED(e, 1);
+  }
+  {
+    StageScope sc(e, ST_COPY);
+    DV_CUDA_OK(cudaMemcpyAsync(s->h_nsp, d_n, sizeof(int) * b, cudaMemcpyDeviceToHost, e->st));
+  }
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  s->cur_ids.assign(frame_ids, frame_ids + b);
+  s->cur_b = b;
+  for (int i = 0; i < b; ++i) {
+    const int sl = s->h_slot[i];
+    s->frame_id[sl] = frame_ids[i];
+    s->n_sp[sl] = s->h_nsp[i];
+    s->n_vio[sl] = n_vio[i];
+  }
+  return DV_OK;
+}
+
+dv_status dv_batch_commit(dv_engine* h, int32_t b, int64_t* first_row) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e->mix || b < 1 || b != e->cur_b || !e->mix_done) { set_error("dv_batch_commit: no extracted batch of this size"); return DV_ERR_INVALID; }
+  const int ws = e->cfg.world_size;
+  int64_t& size = bank_size_ref(e);
+  if (size + (int64_t)ws * b > e->cfg.bank_capacity) { set_error("dv_batch_commit: bank full"); return DV_ERR_CAPACITY; }
+  float* g = mix_gdesc(e);
+  StageScope sc(e, ST_KNN);
+  // this round's queries
+  DV_CUDA_OK(cudaMemcpyAsync(bank_query_buf(e), g, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, e->st));
+  float* dst = bank_rows(e) + size * 512;
+  if (ws == 1) {
+    DV_CUDA_OK(cudaMemcpyAsync(dst, g, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, e->st));
+  } else {
+    // the single collective of the path: rank-major landing == global frame order when frame t -> rank t % P
+    DV_TRY(comm_allgather(e, g, dst, (size_t)512 * b));
+    DV_LAUNCHED(e, 1);
+  }
+  if (first_row) *first_row = size + (int64_t)e->cfg.rank * b;
+  size += (int64_t)ws * b;
+  return DV_OK;
+}
+
+dv_status dv_batch_search(dv_engine* h, int32_t b, const int64_t* nb_limit, float* D, int64_t* I) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (b < 1 || b > e->B || !nb_limit || !D || !I) { set_error("dv_batch_search: bad arguments"); return DV_ERR_INVALID; }
+  return (dv_status)bank_search_device(e, b, nb_limit, e->cfg.knn_k, D, I);
+}
+
+dv_status dv_batch_read_global(dv_engine* h, int32_t i, float* des512) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!e->mix || !e->mix_done || i < 0 || i >= e->cur_b || !des512) { set_error("dv_batch_read_global: no such frame"); return DV_ERR_INVALID; }
+  DV_CUDA_OK(cudaMemcpyAsync(des512, mix_gdesc(e) + (size_t)i * 512, sizeof(float) * 512, cudaMemcpyDeviceToHost, e->st));
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  return DV_OK;
+}
+
+dv_status dv_store_read(dv_engine* h, int64_t frame_id, float* kpts_xy, float* desc, int32_t* n_total, int32_t* n_sp) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  Store* s = e->store;
+  if (frame_id < 0) { set_error("dv_store_read: bad frame id"); return DV_ERR_INVALID; }
+  const int sl = (int)(frame_id % s->slots);
+  if (s->frame_id[sl] != frame_id) { set_error("dv_store_read: keyframe not resident in this rank's store"); return DV_ERR_INVALID; }
+  const int n = s->n_sp[sl] + s->n_vio[sl];
+  if (kpts_xy) DV_CUDA_OK(cudaMemcpyAsync(kpts_xy, s->kpts + (size_t)sl * s->cap * 2, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, e->st));
+  if (desc) DV_CUDA_OK(cudaMemcpyAsync(desc, s->desc + (size_t)sl * s->cap * 256, sizeof(float) * 256 * n, cudaMemcpyDeviceToHost, e->st));
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  if (n_total) *n_total = n;
+  if (n_sp) *n_sp = s->n_sp[sl];
+  return DV_OK;
+}
+
+dv_status dv_batch_match(dv_engine* h, int32_t b, const int64_t* query_ids, const int64_t* old_ids, int32_t* matches,
+                         float* mscores, int32_t* k_out) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  Store* s = e->store;
+  if (!e->lg) { set_error("dv_batch_match: engine created without weights"); return DV_ERR_INVALID; }
+  if (b < 1 || b > e->B || !query_ids || !old_ids || !matches || !mscores || !k_out) { set_error("dv_batch_match: bad arguments"); return DV_ERR_INVALID; }
+  const int V = e->cfg.max_vio;
+  std::vector<LgSeg> segs;
+  std::vector<int> which;
+  for (int i = 0; i < b; ++i) {
+    k_out[i] = 0;
+    const int qs = (int)(query_ids[i] % s->slots), os = (int)(old_ids[i] % s->slots);
+    if (query_ids[i] < 0 || old_ids[i] < 0 || s->frame_id[qs] != query_ids[i] || s->frame_id[os] != old_ids[i]) {
+      set_error("dv_batch_match: keyframe not resident in this rank's store");
+      return DV_ERR_INVALID;
+    }
+    const int m = s->n_vio[qs], n = s->n_sp[os] + s->n_vio[os];
+    // keyframe.cpp:373,:935 - the reference skips SP_RE / LightGlue for <= 20 window points; engine floor is 10
+    if (m < 10 || n < 10) continue;
+    if (n > e->cfg.lg_max_kpts) { set_error("dv_batch_match: old keyframe exceeds lg_max_kpts"); return DV_ERR_CAPACITY; }
+    const float* qk = s->kpts + ((size_t)qs * s->cap + s->n_sp[qs]) * 2;
+    const float* qd = s->desc + ((size_t)qs * s->cap + s->n_sp[qs]) * 256;
+    segs.push_back({qk, qd, m, e->W, e->H, 0});
+    segs.push_back({s->kpts + (size_t)os * s->cap * 2, s->desc + (size_t)os * s->cap * 256, n, e->W, e->H, 0});
+    which.push_back(i);
+  }
+  if (which.empty()) return DV_OK;
+  DV_TRY(lg_run(e, (int)which.size(), segs.data()));
+  for (size_t p = 0; p < which.size(); ++p) {
+    const int i = which[p];
+    DV_TRY(lg_fetch(e, (int)p, V, matches + (size_t)i * V * 2, mscores + (size_t)i * V, nullptr, nullptr, &k_out[i]));
+  }
+  return DV_OK;
+}
+
+}  // extern "C"

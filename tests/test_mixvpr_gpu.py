@@ -1,0 +1,58 @@
+"""MixVPR global descriptor: CUDA path vs the CPU oracle (pre-processing exact, descriptor within fp16 tolerance)."""
+import numpy as np
+import pytest
+
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng(weights_file):
+    from d_vins_b200 import capi
+    e = capi.Engine(height=480, width=752, weights_path=weights_file)
+    yield e
+    e.close()
+
+
+def test_preprocess_matches_reference_kernel_semantics(eng):
+    from oracle import mixvpr as omix, synth
+    img = synth.make_frame(480, 752, synth.BASE_SEED)
+    eng.frame_upload(img)
+    eng.mix_describe()
+    got = eng.dbg_read("mix_img").reshape(320, 320, 3)
+    ref = omix.preprocess_mix(img).transpose(1, 2, 0)
+    # the device stores the pre-processed image as fp16: identical after the same rounding
+    assert np.array_equal(got, ref.astype(np.float16).astype(np.float32))
+
+
+def test_mixvpr_descriptor(eng, all_weights):
+    from oracle import mixvpr as omix, synth, weights
+    wm = weights.sub(all_weights, "mix.")
+    for seed in (synth.BASE_SEED, synth.BASE_SEED + 17):
+        img = synth.make_frame(480, 752, seed)
+        keep = {}
+        ref = omix.mixvpr(wm, img, keep)
+        eng.frame_upload(img)
+        got = eng.mix_describe()
+        feat = eng.dbg_read("mix_feat").reshape(400, 1024)
+        rf = parity.nhwc(keep["layer3.5"]).reshape(400, 1024)
+        assert np.abs(feat - rf).max() < 0.03 * np.abs(rf).max(), np.abs(feat - rf).max()
+        assert abs(np.linalg.norm(got) - 1.0) < 1e-5
+        cos = float(ref @ got)
+        assert cos > parity.GLOBAL_COS_MIN, cos
+        assert np.abs(ref - got).max() < 4e-3, np.abs(ref - got).max()
+
+
+def test_mixvpr_bgr_input(eng, all_weights):
+    """3-channel frames: the BGR->RGB swap + BGR-ordered mean/std quirk (deep_net.cpp:1298-1300) is replicated."""
+    from oracle import mixvpr as omix, weights
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (480, 752, 3), dtype=np.uint8)
+    eng.frame_upload(img)
+    got = eng.mix_describe()
+    pre = eng.dbg_read("mix_img").reshape(320, 320, 3)
+    ref_pre = omix.preprocess_mix(img).transpose(1, 2, 0)
+    assert np.array_equal(pre, ref_pre.astype(np.float16).astype(np.float32))
+    ref = omix.mixvpr(weights.sub(all_weights, "mix."), img)
+    assert float(ref @ got) > parity.GLOBAL_COS_MIN
