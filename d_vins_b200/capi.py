@@ -246,6 +246,14 @@ class Engine:
         names = ["sp_convs", "sp_post", "mixvpr", "knn", "lightglue", "copies"]
         return dict(zip(names, list(ms))), n.value
 
+    def probe_enable(self, on=True):
+        _chk(_lib.dv_probe_enable(self._h, 1 if on else 0))
+
+    def probe_read(self, reset=True):
+        ms = C.c_double(0); n = C.c_int64(0)
+        _chk(_lib.dv_probe_read(self._h, C.byref(ms), C.byref(n), 1 if reset else 0))
+        return ms.value, n.value
+
     # ---------------------------------------------------------------- stage-level
     def dbg_gemm(self, A, B, bias=None, relu=False):
         A, B = _f32(A), _f32(B)

@@ -119,6 +119,7 @@ void dv_destroy(dv_engine* h) {
   for (void* p : e->allocs) cudaFree(p);
   for (void* p : e->pinned) cudaFreeHost(p);
   for (auto& p : e->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto& p : e->probe_pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   if (e->ev_t0) cudaEventDestroy(e->ev_t0);
   if (e->ev_t1) cudaEventDestroy(e->ev_t1);
@@ -170,6 +171,30 @@ dv_status dv_stats_read(dv_engine* h, double* stage_ms6, int64_t* launches) {
   drain_stats(e);
   if (stage_ms6) for (int i = 0; i < ST_COUNT; ++i) stage_ms6[i] = e->stage_ms[i];
   if (launches) *launches = e->launches;
+  return DV_OK;
+}
+
+dv_status dv_probe_enable(dv_engine* h, int32_t on) {
+  DV_CHECK_ENGINE(h);
+  reinterpret_cast<Engine*>(h)->probe_on = on != 0;
+  return DV_OK;
+}
+dv_status dv_probe_read(dv_engine* h, double* ms, int64_t* launches, int32_t reset) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  for (auto& p : e->probe_pending) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, p.a, p.b);
+    e->probe_ms += t;
+    e->probe_n++;
+    e->ev_pool.push_back(p.a);
+    e->ev_pool.push_back(p.b);
+  }
+  e->probe_pending.clear();
+  if (ms) *ms = e->probe_ms;
+  if (launches) *launches = e->probe_n;
+  if (reset) { e->probe_ms = 0; e->probe_n = 0; }
   return DV_OK;
 }
 

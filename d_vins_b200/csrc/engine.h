@@ -63,6 +63,9 @@ struct Engine {
   struct Pending { int stage; cudaEvent_t a, b; };
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> ev_pool;
+  bool probe_on = false;
+  double probe_ms = 0; int64_t probe_n = 0;
+  std::vector<Pending> probe_pending;
 
   // debug tensors by name: device pointer + element count + dtype (0 f32, 1 f16, 2 i32)
   struct Dbg { const void* p; int64_t n; int dtype; };
@@ -94,6 +97,11 @@ struct Engine {
 };
 
 // stage timing scope (no-op unless stats are enabled)
+struct ProbeScope {   // event pair around one kernel launch (dominant-kernel roofline probe)
+  Engine* e; cudaEvent_t a = nullptr, b = nullptr;
+  explicit ProbeScope(Engine* e_);
+  ~ProbeScope();
+};
 struct StageScope {
   Engine* e; int stage; cudaEvent_t a = nullptr, b = nullptr;
   StageScope(Engine* e_, int s);

@@ -500,7 +500,10 @@ int sp_run_encoder(Engine* e, int b) {
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
   k_conv1a<<<dim3(cdiv(W, 128), H, b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
   DV_CUDA_OK(cudaGetLastError());
-  DV_TRY(launch_gemm(s->p1b, b, e->st));
+  {
+    ProbeScope pr(e);
+    DV_TRY(launch_gemm(s->p1b, b, e->st));
+  }
   DV_TRY(launch_gemm(s->p2a, b, e->st));
   DV_TRY(launch_gemm(s->p2b, b, e->st));
   DV_TRY(launch_gemm(s->p3a, b, e->st));

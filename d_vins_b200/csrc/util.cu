@@ -59,4 +59,21 @@ StageScope::~StageScope() {
   e->pending.push_back({stage, a, b});
 }
 
+ProbeScope::ProbeScope(Engine* e_) : e(e_) {
+  if (!e->probe_on) return;
+  auto get = [&]() {
+    cudaEvent_t ev;
+    if (!e->ev_pool.empty()) { ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+    else cudaEventCreate(&ev);
+    return ev;
+  };
+  a = get(); b = get();
+  cudaEventRecord(a, e->st);
+}
+ProbeScope::~ProbeScope() {
+  if (!a) return;
+  cudaEventRecord(b, e->st);
+  e->probe_pending.push_back({0, a, b});
+}
+
 }  // namespace dv

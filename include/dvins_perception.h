@@ -153,6 +153,10 @@ dv_status dv_sync(dv_engine* e);
 dv_status dv_stats_reset(dv_engine* e);
 dv_status dv_stats_read(dv_engine* e, double* stage_ms6, int64_t* launches);
 dv_status dv_stats_enable(dv_engine* e, int32_t on);   /* stage timing costs event records; off by default */
+/* Event pair around every launch of the dominant kernel (conv1b implicit GEMM, 43 % of SuperPoint's MACs): its
+ * accumulated device time and launch count inside the caller's timed region -> roofline.achieved in bench.py. */
+dv_status dv_probe_enable(dv_engine* e, int32_t on);
+dv_status dv_probe_read(dv_engine* e, double* ms, int64_t* launches, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage-level entry points (parity tests address every kernel family in isolation through these).

@@ -1,0 +1,61 @@
+"""The C-ABI shared library loads on a CPU-only box, exports every symbol include/dvins_perception.h declares,
+and refuses to run without a GPU (no CPU fallback).  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dvins_perception.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from d_vins_b200 import build
+    lib = ctypes.CDLL(build.build())
+    names = _declared()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+
+
+def test_config_default_and_struct_size():
+    from d_vins_b200 import capi
+    cfg = capi.default_config()
+    assert cfg.struct_size == ctypes.sizeof(capi.DvConfig)
+    assert (cfg.height, cfg.width, cfg.max_kpts, cfg.knn_k, cfg.exclude_recent) == (480, 752, 512, 3, 50)
+    assert abs(cfg.det_thresh - 0.0005) < 1e-8 and abs(cfg.lg_filter_thresh - 0.1) < 1e-7
+
+
+def test_no_cpu_fallback():
+    import torch
+    from d_vins_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.DvError) as ei:
+        capi.Engine()
+    assert ei.value.status == 7          # DV_ERR_NOGPU
+
+
+def test_bad_config_rejected_before_touching_cuda():
+    from d_vins_b200 import capi
+    cfg = capi.default_config()
+    cfg.struct_size = 4
+    h = ctypes.c_void_p()
+    assert capi._lib.dv_create(ctypes.byref(cfg), ctypes.byref(h)) == 1     # DV_ERR_INVALID
+    assert b"size mismatch" in capi._lib.dv_last_error()
+
+
+def test_product_never_imports_oracle():
+    """The product package must not import, call or link anything under oracle/."""
+    pkg = os.path.join(ROOT, "d_vins_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
