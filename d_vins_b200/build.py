@@ -83,5 +83,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_shim_demo() -> str:
+    """g++ build of the reference-facing C++ facade (csrc/shim) + the keyframe.cpp-order demo driver."""
+    lib = LIB if os.path.exists(LIB) else build()
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "shim_demo")
+    srcs = [os.path.join(CSRC, "shim", "deep_net_shim.cpp"),
+            os.path.join(os.path.dirname(HERE), "tests", "cpp", "shim_demo.cpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(x) > os.path.getmtime(exe) for x in srcs + [lib]):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe] + srcs + [
+            "-L" + HERE, "-ldvins_b200", "-Wl,-rpath," + HERE]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("shim build failed")
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

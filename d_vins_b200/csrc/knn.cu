@@ -11,8 +11,9 @@
 namespace dv {
 
 #define KNN_MAXK 8
-#define KNN_QB 4             // queries processed per pass over the bank
+#define KNN_QB 8             // queries processed per pass over the bank (query vectors live in shared memory)
 #define KNN_WARPS 8
+#define KNN_RPW 4            // bank rows in flight per warp (16 x 128-bit loads per lane)
 #define KNN_ROWS_PER_BLOCK 64
 
 struct Bank {
@@ -34,103 +35,145 @@ __device__ __forceinline__ bool better(float d1, long long i1, float d2, long lo
   return d1 > d2 || (d1 == d2 && i1 < i2);
 }
 
-__device__ __forceinline__ void topk_insert(float* D, long long* I, int k, float d, long long i) {
-  if (!better(d, i, D[k - 1], I[k - 1])) return;
-  int p = k - 1;
-  while (p > 0 && better(d, i, D[p - 1], I[p - 1])) { D[p] = D[p - 1]; I[p] = I[p - 1]; --p; }
-  D[p] = d; I[p] = i;
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&D)[K], long long (&I)[K], float d, long long i) {
+  if (!better(d, i, D[K - 1], I[K - 1])) return;
+  D[K - 1] = d; I[K - 1] = i;
+#pragma unroll
+  for (int p = K - 1; p > 0; --p) {
+    if (better(D[p], I[p], D[p - 1], I[p - 1])) {
+      const float td = D[p]; D[p] = D[p - 1]; D[p - 1] = td;
+      const long long ti = I[p]; I[p] = I[p - 1]; I[p - 1] = ti;
+    }
+  }
 }
 
-// grid: (nblocks, ceil(nq / KNN_QB)).  Each block scans KNN_ROWS_PER_BLOCK rows for up to KNN_QB queries.
+// Streaming scan: grid (nblocks, ceil(nq / KNN_QB)).  Each warp keeps KNN_RPW bank rows (4 x 2 KB) in flight in
+// registers; the 8 query vectors sit in shared memory.  The 32 partial dot products (4 rows x 8 queries) of a lane
+// are reduced across the warp with a 31-shuffle butterfly that leaves lane L holding the total of pair L, so lane L
+// owns the candidate list of query (L & 7) for row slot (L >> 3).
+template <int K>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_scan(const float* __restrict__ bank,
                                                             const float* __restrict__ q,
-                                                            const long long* __restrict__ nb_limit, int nq, int k,
+                                                            const long long* __restrict__ nb_limit, int nq,
                                                             float* __restrict__ partD, long long* __restrict__ partI,
                                                             int nblocks) {
-  __shared__ float sD[KNN_QB][KNN_WARPS][KNN_MAXK];
-  __shared__ long long sI[KNN_QB][KNN_WARPS][KNN_MAXK];
+  __shared__ __align__(16) float sq[KNN_QB][512];
+  __shared__ float sD[KNN_QB][KNN_WARPS * 4][K];
+  __shared__ long long sI[KNN_QB][KNN_WARPS * 4][K];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.y * KNN_QB;
   const int nqb = min(KNN_QB, nq - q0);
-  // each lane owns 16 of the 512 dims: 4 float4 at lane*4 + {0,128,256,384}
-  float4 qr[KNN_QB][4];
-  long long lim[KNN_QB];
-  long long maxlim = 0;
-#pragma unroll
-  for (int j = 0; j < KNN_QB; ++j) {
-    lim[j] = (j < nqb) ? nb_limit[q0 + j] : 0;
-    maxlim = max(maxlim, lim[j]);
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      qr[j][c] = (j < nqb) ? __ldg(reinterpret_cast<const float4*>(q + (int64_t)(q0 + j) * 512) + c * 32 + lane)
-                           : make_float4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < KNN_QB * 128; i += blockDim.x) {
+    const int j = i >> 7, c = i & 127;
+    reinterpret_cast<float4*>(&sq[j][0])[c] =
+        (j < nqb) ? __ldg(reinterpret_cast<const float4*>(q + (int64_t)(q0 + j) * 512) + c) : make_float4(0, 0, 0, 0);
   }
-  float D[KNN_QB][KNN_MAXK];
-  long long I[KNN_QB][KNN_MAXK];
+  long long maxlim = 0;
+  for (int j = 0; j < nqb; ++j) maxlim = max(maxlim, nb_limit[q0 + j]);
+  const int myq = lane & 7, myslot = lane >> 3;
+  const long long mylim = (myq < nqb) ? nb_limit[q0 + myq] : 0;
+  float D[K]; long long I[K];
 #pragma unroll
-  for (int j = 0; j < KNN_QB; ++j)
-#pragma unroll
-    for (int t = 0; t < KNN_MAXK; ++t) { D[j][t] = -INFINITY; I[j][t] = -1; }
+  for (int t = 0; t < K; ++t) { D[t] = -INFINITY; I[t] = -1; }
+  __syncthreads();
   const long long r0 = (long long)blockIdx.x * KNN_ROWS_PER_BLOCK;
   const long long r1 = min(r0 + KNN_ROWS_PER_BLOCK, maxlim);
-  for (long long r = r0 + warp; r < r1; r += KNN_WARPS) {
-    const float4* row = reinterpret_cast<const float4*>(bank + r * 512);
-    float4 v[4];
+  for (long long r = r0 + warp * KNN_RPW; r < r1; r += KNN_WARPS * KNN_RPW) {
+    float4 v[KNN_RPW][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = __ldg(row + c * 32 + lane);
+    for (int rr = 0; rr < KNN_RPW; ++rr) {
+      const float4* row = reinterpret_cast<const float4*>(bank + (r + rr) * 512);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[rr][c] = (r + rr < r1) ? __ldg(row + c * 32 + lane) : make_float4(0, 0, 0, 0);
+    }
+    float s[32];   // index = rr * 8 + j
 #pragma unroll
     for (int j = 0; j < KNN_QB; ++j) {
-      float s = 0.f;
+      float4 qv[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        s += v[c].x * qr[j][c].x + v[c].y * qr[j][c].y + v[c].z * qr[j][c].z + v[c].w * qr[j][c].w;
+      for (int c = 0; c < 4; ++c) qv[c] = reinterpret_cast<const float4*>(&sq[j][0])[c * 32 + lane];
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (j < nqb && r < lim[j]) topk_insert(D[j], I[j], k, s, r);   // every lane keeps the same (uniform) list
+      for (int rr = 0; rr < KNN_RPW; ++rr) {
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          a += v[rr][c].x * qv[c].x + v[rr][c].y * qv[c].y + v[rr][c].z * qv[c].z + v[rr][c].w * qv[c].w;
+        s[rr * 8 + j] = a;
+      }
     }
-  }
-  if (lane == 0) {
+    // butterfly transpose-reduce: after the 5 steps lane L holds sum over lanes of s[L]
 #pragma unroll
-    for (int j = 0; j < KNN_QB; ++j)
-      for (int t = 0; t < k; ++t) { sD[j][warp][t] = D[j][t]; sI[j][warp][t] = I[j][t]; }
+    for (int h = 16; h >= 1; h >>= 1) {
+      const bool up = (lane & h) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const float keep = up ? s[i + h] : s[i];
+        const float send = up ? s[i] : s[i + h];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+      }
+    }
+    const long long row = r + myslot;
+    if (row < mylim) topk_insert<K>(D, I, s[0], row);
   }
+#pragma unroll
+  for (int t = 0; t < K; ++t) { sD[myq][warp * 4 + myslot][t] = D[t]; sI[myq][warp * 4 + myslot][t] = I[t]; }
   __syncthreads();
   if (threadIdx.x < nqb) {
     const int j = threadIdx.x;
-    float bD[KNN_MAXK]; long long bI[KNN_MAXK];
-    for (int t = 0; t < k; ++t) { bD[t] = -INFINITY; bI[t] = -1; }
-    for (int w = 0; w < KNN_WARPS; ++w)
-      for (int t = 0; t < k; ++t)
-        if (sI[j][w][t] >= 0) topk_insert(bD, bI, k, sD[j][w][t], sI[j][w][t]);
-    for (int t = 0; t < k; ++t) {
-      partD[((int64_t)(q0 + j) * nblocks + blockIdx.x) * k + t] = bD[t];
-      partI[((int64_t)(q0 + j) * nblocks + blockIdx.x) * k + t] = bI[t];
+    float bD[K]; long long bI[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) { bD[t] = -INFINITY; bI[t] = -1; }
+    for (int w = 0; w < KNN_WARPS * 4; ++w)
+#pragma unroll
+      for (int t = 0; t < K; ++t)
+        if (sI[j][w][t] >= 0) topk_insert<K>(bD, bI, sD[j][w][t], sI[j][w][t]);
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      partD[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bD[t];
+      partI[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bI[t];
     }
   }
 }
 
-// one block per query: merge nblocks partial lists
+// one block per query: merge nblocks partial lists (strided gather, then a shared-memory tree)
+template <int K>
 __global__ void __launch_bounds__(256) k_knn_merge(const float* __restrict__ partD, const long long* __restrict__ partI,
-                                                   int nblocks, int k, float* __restrict__ outD,
+                                                   int nblocks, float* __restrict__ outD,
                                                    long long* __restrict__ outI) {
-  __shared__ float sD[256][KNN_MAXK];
-  __shared__ long long sI[256][KNN_MAXK];
+  __shared__ float sD[256][K];
+  __shared__ long long sI[256][K];
   const int qi = blockIdx.x, tid = threadIdx.x;
-  float D[KNN_MAXK]; long long I[KNN_MAXK];
-  for (int t = 0; t < k; ++t) { D[t] = -INFINITY; I[t] = -1; }
+  float D[K]; long long I[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) { D[t] = -INFINITY; I[t] = -1; }
   for (int b = tid; b < nblocks; b += 256)
-    for (int t = 0; t < k; ++t) {
-      const long long i = partI[((int64_t)qi * nblocks + b) * k + t];
-      if (i >= 0) topk_insert(D, I, k, partD[((int64_t)qi * nblocks + b) * k + t], i);
+#pragma unroll
+    for (int t = 0; t < K; ++t) {
+      const long long i = partI[((int64_t)qi * nblocks + b) * K + t];
+      if (i >= 0) topk_insert<K>(D, I, partD[((int64_t)qi * nblocks + b) * K + t], i);
     }
-  for (int t = 0; t < k; ++t) { sD[tid][t] = D[t]; sI[tid][t] = I[t]; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 256; ++w)
-      for (int t = 0; t < k; ++t)
-        if (sI[w][t] >= 0) topk_insert(D, I, k, sD[w][t], sI[w][t]);
-    for (int t = 0; t < k; ++t) { outD[(int64_t)qi * k + t] = D[t]; outI[(int64_t)qi * k + t] = I[t]; }
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+#pragma unroll
+    for (int t = 0; t < K; ++t) { sD[tid][t] = D[t]; sI[tid][t] = I[t]; }
+    __syncthreads();
+    if (tid < stride) {
+#pragma unroll
+      for (int t = 0; t < K; ++t)
+        if (sI[tid + stride][t] >= 0) topk_insert<K>(D, I, sD[tid + stride][t], sI[tid + stride][t]);
+    }
+    __syncthreads();
   }
+  if (tid == 0)
+#pragma unroll
+    for (int t = 0; t < K; ++t) { outD[(int64_t)qi * K + t] = D[t]; outI[(int64_t)qi * K + t] = I[t]; }
+}
+
+template <int K>
+static void knn_launch(const float* rows, const float* q, const long long* d_nb, int nq, int nblocks, float* partD,
+                       long long* partI, float* outD, long long* outI, cudaStream_t st) {
+  k_knn_scan<K><<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, st>>>(rows, q, d_nb, nq, partD, partI, nblocks);
+  k_knn_merge<K><<<nq, 256, 0, st>>>(partD, partI, nblocks, outD, outI);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -177,9 +220,16 @@ int bank_search_device(Engine* e, int nq, const int64_t* nb_limit, int k, float*
   }
   DV_CUDA_OK(cudaMemcpyAsync(b->d_nb, b->h_nb, sizeof(long long) * nq, cudaMemcpyHostToDevice, e->st));
   const int nblocks = (int)cdiv64(maxlim, KNN_ROWS_PER_BLOCK);
-  k_knn_scan<<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, e->st>>>(b->rows, b->q, b->d_nb, nq, k, b->partD,
-                                                                          b->partI, nblocks);
-  k_knn_merge<<<nq, 256, 0, e->st>>>(b->partD, b->partI, nblocks, k, b->outD, b->outI);
+  switch (k) {
+    case 1: knn_launch<1>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 2: knn_launch<2>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 3: knn_launch<3>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 4: knn_launch<4>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 5: knn_launch<5>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 6: knn_launch<6>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 7: knn_launch<7>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    default: knn_launch<8>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+  }
   DV_CUDA_OK(cudaGetLastError());
   DV_LAUNCHED(e, 2);
   DV_CUDA_OK(cudaMemcpyAsync(b->h_D, b->outD, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, e->st));

@@ -136,8 +136,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 
 __global__ void __launch_bounds__(128) k_lg_attention(const AttnJob* __restrict__ jobs, float scale) {
   __shared__ __align__(16) __half sQ[64 * ATT_LD];
-  __shared__ __align__(16) __half sK[64 * ATT_LD];
-  __shared__ __align__(16) __half sV[64 * ATT_LD];
+  __shared__ __align__(16) __half sKb[2][64 * ATT_LD];   // double-buffered K / V chunks (cp.async)
+  __shared__ __align__(16) __half sVb[2][64 * ATT_LD];
   const AttnJob jb = jobs[blockIdx.z];
   const int q0 = blockIdx.x * 64;
   if (q0 >= jb.nq) return;
@@ -166,19 +166,33 @@ __global__ void __launch_bounds__(128) k_lg_attention(const AttnJob* __restrict_
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
   const float sl2 = scale * 1.4426950408889634f;   // softmax in base 2
-  for (int k0 = 0; k0 < jb.nk; k0 += 64) {
-    __syncthreads();
+  // stage loader: 16-byte cp.async per (row, 8-half column group); rows >= nk are zero-filled (src-size 0)
+  auto load_kv = [&](int stage, int k0) {
     for (int i = tid; i < 64 * 8; i += 128) {
       const int r = i >> 3, c = (i & 7) * 8;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (k0 + r < jb.nk) {
-        kv = __ldg(reinterpret_cast<const uint4*>(K + (int64_t)(k0 + r) * jb.ldk + c));
-        vv = __ldg(reinterpret_cast<const uint4*>(V + (int64_t)(k0 + r) * jb.ldv + c));
-      }
-      *reinterpret_cast<uint4*>(&sK[r * ATT_LD + c]) = kv;
-      *reinterpret_cast<uint4*>(&sV[r * ATT_LD + c]) = vv;
+      const bool ok = k0 + r < jb.nk;
+      const int rr = ok ? k0 + r : 0;
+      const uint32_t dk = (uint32_t)__cvta_generic_to_shared(&sKb[stage][r * ATT_LD + c]);
+      const uint32_t dv = (uint32_t)__cvta_generic_to_shared(&sVb[stage][r * ATT_LD + c]);
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dk), "l"(K + (int64_t)rr * jb.ldk + c), "r"(sz) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dv), "l"(V + (int64_t)rr * jb.ldv + c), "r"(sz) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int n_it = (jb.nk + 63) >> 6;
+  load_kv(0, 0);
+  for (int it = 0; it < n_it; ++it) {
+    const int k0 = it * 64;
+    if (it + 1 < n_it) {
+      load_kv((it + 1) & 1, k0 + 64);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const __half* sK = sKb[it & 1];
+    const __half* sV = sVb[it & 1];
     // S = Q K^T : 16 x 64 per warp
     float s[8][4];
 #pragma unroll
@@ -250,6 +264,7 @@ __global__ void __launch_bounds__(128) k_lg_attention(const AttnJob* __restrict_
         mma16816(o[dp * 2 + 1], pa, b2, b3);
       }
     }
+    __syncthreads();   // everyone is done with this stage before the next prefetch overwrites it
   }
   // finalise: row sums across the quad, normalise, store fp16
 #pragma unroll

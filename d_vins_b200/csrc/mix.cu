@@ -217,30 +217,42 @@ __global__ void k_layernorm_f2h(const float* __restrict__ x, const float* __rest
   for (int i = lane; i < D; i += 32) out[row * D + i] = __float2half_rn((xr[i] - mean) * rstd * g[i] + bta[i]);
 }
 
-// row_proj (400 -> 2) on y [B,400,256], flatten index c*2 + r, L2-normalise -> [B,512].  One block per frame.
-__global__ void __launch_bounds__(256) k_rowproj_norm(const float* __restrict__ y, const float* __restrict__ w,
-                                                      const float* __restrict__ bias, float* __restrict__ out, int P) {
+// row_proj (400 -> 2) on y [B,400,256], flatten index c*2 + r, L2-normalise -> [B,512].  One block per frame:
+// 4 thread groups split the 400 positions (coalesced 1 KB rows), shared-memory combine, block-wide norm.
+__global__ void __launch_bounds__(1024) k_rowproj_norm(const float* __restrict__ y, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int P) {
+  __shared__ float part[4][256][2];
   __shared__ float red[8];
-  const int b = blockIdx.x, o = threadIdx.x;
+  const int b = blockIdx.x, o = threadIdx.x & 255, grp = threadIdx.x >> 8;
   float a0 = 0.f, a1 = 0.f;
-  for (int p = 0; p < P; ++p) {
+  const int per = (P + 3) / 4;
+  const int p0 = grp * per, p1 = min(P, p0 + per);
+#pragma unroll 4
+  for (int p = p0; p < p1; ++p) {
     const float v = y[((int64_t)b * P + p) * 256 + o];
     a0 = fmaf(v, __ldg(w + p), a0);
     a1 = fmaf(v, __ldg(w + P + p), a1);
   }
-  a0 += bias[0];
-  a1 += bias[1];
-  float ss = a0 * a0 + a1 * a1;
-#pragma unroll
-  for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-  if ((o & 31) == 0) red[o >> 5] = ss;
+  part[grp][o][0] = a0;
+  part[grp][o][1] = a1;
   __syncthreads();
-  float tot = 0.f;
+  if (grp == 0) {
+    a0 = ((part[0][o][0] + part[1][o][0]) + (part[2][o][0] + part[3][o][0])) + bias[0];
+    a1 = ((part[0][o][1] + part[1][o][1]) + (part[2][o][1] + part[3][o][1])) + bias[1];
+    float ss = a0 * a0 + a1 * a1;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i];
-  const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
-  out[(int64_t)b * 512 + o * 2 + 0] = a0 * inv;
-  out[(int64_t)b * 512 + o * 2 + 1] = a1 * inv;
+    for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((o & 31) == 0) red[o >> 5] = ss;
+  }
+  __syncthreads();
+  if (grp == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+    out[(int64_t)b * 512 + o * 2 + 0] = a0 * inv;
+    out[(int64_t)b * 512 + o * 2 + 1] = a1 * inv;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -489,7 +501,7 @@ int mix_init(Engine* e) {
     DV_TRY(e->upload_f32(br->data, &m->row_b));
     m->ops.push_back([](Engine* en, int b) {
       MixNet* mm = en->mix;
-      k_rowproj_norm<<<b, 256, 0, en->st>>>(mm->y32, mm->row_w, mm->row_b, mm->gdesc, 400);
+      k_rowproj_norm<<<b, 1024, 0, en->st>>>(mm->y32, mm->row_w, mm->row_b, mm->gdesc, 400);
       return (int)DV_OK;
     });
     m->n_launch++;

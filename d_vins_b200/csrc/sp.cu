@@ -53,16 +53,18 @@ __global__ void k_gray(const uint8_t* __restrict__ img, float* __restrict__ out,
 }
 
 // conv1a: C_in = 1 is not an MMA shape -> CUDA cores.  8 threads per pixel, 8 output channels each: a warp writes
-// 4 pixels x 128 B = 512 contiguous bytes of the NHWC fp16 output.
+// 4 pixels x 128 B = 512 contiguous bytes of the NHWC fp16 output.  A block covers 128 x CONV1A_ROWS pixels so the
+// 72 filter taps each thread needs are loaded once per block.
+#define CONV1A_ROWS 8
 __global__ void __launch_bounds__(256) k_conv1a(const float* __restrict__ gray, const float* __restrict__ w,
                                                 const float* __restrict__ bias, __half* __restrict__ out, int H,
                                                 int W) {
-  __shared__ float tile[3][130];
-  const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 128;
+  __shared__ float tile[CONV1A_ROWS + 2][130];
+  const int b = blockIdx.z, y0 = blockIdx.y * CONV1A_ROWS, x0 = blockIdx.x * 128;
   const float* g = gray + (int64_t)b * H * W;
-  for (int i = threadIdx.x; i < 3 * 130; i += 256) {
+  for (int i = threadIdx.x; i < (CONV1A_ROWS + 2) * 130; i += 256) {
     const int r = i / 130, c = i - r * 130;
-    const int yy = y + r - 1, xx = x0 + c - 1;
+    const int yy = y0 + r - 1, xx = x0 + c - 1;
     tile[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? g[(int64_t)yy * W + xx] : 0.f;
   }
   const int cg = threadIdx.x & 7, px = threadIdx.x >> 3;
@@ -74,25 +76,29 @@ __global__ void __launch_bounds__(256) k_conv1a(const float* __restrict__ gray, 
     for (int t = 0; t < 9; ++t) wr[c][t] = w[(cg * 8 + c) * 9 + t];
   }
   __syncthreads();
+  for (int ry = 0; ry < CONV1A_ROWS; ++ry) {
+    const int y = y0 + ry;
+    if (y >= H) break;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int xl = px + it * 32;
-    const int x = x0 + xl;
-    if (x >= W) continue;
-    float in[9];
+    for (int it = 0; it < 4; ++it) {
+      const int xl = px + it * 32;
+      const int x = x0 + xl;
+      if (x >= W) continue;
+      float in[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) in[r * 3 + s] = tile[r][xl + s];
-    __align__(16) __half2 hv[4];
+        for (int q = 0; q < 3; ++q) in[r * 3 + q] = tile[ry + r][xl + q];
+      __align__(16) __half2 hv[4];
 #pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-      float a0 = br[c], a1 = br[c + 1];
+      for (int c = 0; c < 8; c += 2) {
+        float a0 = br[c], a1 = br[c + 1];
 #pragma unroll
-      for (int t = 0; t < 9; ++t) { a0 = fmaf(wr[c][t], in[t], a0); a1 = fmaf(wr[c + 1][t], in[t], a1); }
-      hv[c >> 1] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+        for (int t = 0; t < 9; ++t) { a0 = fmaf(wr[c][t], in[t], a0); a1 = fmaf(wr[c + 1][t], in[t], a1); }
+        hv[c >> 1] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+      }
+      *reinterpret_cast<uint4*>(out + (((int64_t)b * H + y) * W + x) * 64 + cg * 8) = *reinterpret_cast<uint4*>(hv);
     }
-    *reinterpret_cast<uint4*>(out + (((int64_t)b * H + y) * W + x) * 64 + cg * 8) = *reinterpret_cast<uint4*>(hv);
   }
 }
 
@@ -132,27 +138,55 @@ __global__ void k_softmax_d2s(const float* __restrict__ logits, int ld, float* _
 #define NMS_RH (NMS_TH + 2 * NMS_HALO)
 #define NMS_RN (NMS_RW * NMS_RH)
 
+// 9-tap running max over a strip of L outputs in registers: 4 max ops per output (pairwise doubling) and ONE shared
+// memory load per input instead of 9.  Taps outside [0, n) are -inf (region edge == torch's implicit -inf padding).
+template <int L>
+__device__ __forceinline__ void strip_max9(const float* __restrict__ in, float* __restrict__ out, int stride, int p0,
+                                           int n) {
+  float v[L + 8];
+#pragma unroll
+  for (int i = 0; i < L + 8; ++i) {
+    const int p = p0 + i - 4;
+    v[i] = (p >= 0 && p < n) ? in[p * stride] : -INFINITY;
+  }
+  float m2[L + 7];
+#pragma unroll
+  for (int i = 0; i < L + 7; ++i) m2[i] = fmaxf(v[i], v[i + 1]);
+  float m4[L + 5];
+#pragma unroll
+  for (int i = 0; i < L + 5; ++i) m4[i] = fmaxf(m2[i], m2[i + 2]);
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const float m8 = fmaxf(m4[i], m4[i + 4]);
+    if (p0 + i < n) out[(p0 + i) * stride] = fmaxf(m8, v[i + 8]);
+  }
+}
+
+#define NMS_THREADS 320
+#define NMS_ROW_STRIP 26     // 104 = 4 x 26
+#define NMS_COL_STRIP 24     // 72  = 3 x 24
+
 __device__ __forceinline__ void maxpool9_inplace(float* T2, float* T1) {
-  // T1 = rowmax(T2); T2 = colmax(T1).  Out-of-region taps are skipped (region edge == -inf padding).
-  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
-    const int y = i / NMS_RW, x = i - y * NMS_RW;
-    const int lo = max(x - 4, 0), hi = min(x + 4, NMS_RW - 1);
-    float m = T2[y * NMS_RW + lo];
-    for (int xx = lo + 1; xx <= hi; ++xx) m = fmaxf(m, T2[y * NMS_RW + xx]);
-    T1[i] = m;
+  // T1 = rowmax(T2); T2 = colmax(T1)
+  {
+    const int t = threadIdx.x;
+    if (t < NMS_RH * (NMS_RW / NMS_ROW_STRIP)) {
+      const int row = t / (NMS_RW / NMS_ROW_STRIP), sp = t - row * (NMS_RW / NMS_ROW_STRIP);
+      strip_max9<NMS_ROW_STRIP>(T2 + row * NMS_RW, T1 + row * NMS_RW, 1, sp * NMS_ROW_STRIP, NMS_RW);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
-    const int y = i / NMS_RW, x = i - y * NMS_RW;
-    const int lo = max(y - 4, 0), hi = min(y + 4, NMS_RH - 1);
-    float m = T1[lo * NMS_RW + x];
-    for (int yy = lo + 1; yy <= hi; ++yy) m = fmaxf(m, T1[yy * NMS_RW + x]);
-    T2[i] = m;
+  {
+    const int t = threadIdx.x;
+    if (t < NMS_RW * (NMS_RH / NMS_COL_STRIP)) {
+      const int sp = t / NMS_RW, col = t - sp * NMS_RW;
+      strip_max9<NMS_COL_STRIP>(T1 + col, T2 + col, NMS_RW, sp * NMS_COL_STRIP, NMS_RH);
+    }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_nms_select(const float* __restrict__ smap, float* __restrict__ nms_out,
+__global__ void __launch_bounds__(NMS_THREADS) k_nms_select(const float* __restrict__ smap, float* __restrict__ nms_out,
                                                     unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
                                                     int H8, int W8, int border, float thresh) {
   extern __shared__ float sm[];
@@ -498,7 +532,7 @@ int sp_run_encoder(Engine* e, int b) {
   const int H = e->H, W = e->W;
   const int64_t npix = (int64_t)b * H * W;
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
-  k_conv1a<<<dim3(cdiv(W, 128), H, b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
+  k_conv1a<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
   DV_CUDA_OK(cudaGetLastError());
   {
     ProbeScope pr(e);
@@ -522,7 +556,7 @@ static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
   SpNet* s = e->sp;
   const int H8 = s->H8, W8 = s->W8, K = e->cfg.max_kpts;
   DV_CUDA_OK(cudaMemsetAsync(s->cand_cnt, 0, sizeof(int) * b, e->st));
-  k_nms_select<<<dim3(cdiv(W8, NMS_TW), cdiv(H8, NMS_TH), b), 256, NMS_RN * (3 * 4 + 2), e->st>>>(
+  k_nms_select<<<dim3(cdiv(W8, NMS_TW), cdiv(H8, NMS_TH), b), NMS_THREADS, NMS_RN * (3 * 4 + 2), e->st>>>(
       smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
   k_topk<<<b, 1024, 0, e->st>>>(s->cand, s->cand_cnt, H8 * W8, K, W8, s->kpts, s->kpts_f, s->scores, s->n_kpts);
   DV_CUDA_OK(cudaGetLastError());
