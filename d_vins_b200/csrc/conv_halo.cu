@@ -1,0 +1,231 @@
+// Weights-stationary, halo-tile 3x3 convolution (64 -> 64 channels) on tcgen05 - the SuperPoint conv1b / conv2a /
+// conv2b layers (65 % of SuperPoint's MACs).
+//
+// Why: the tap-per-TMA implicit GEMM (gemm_umma.cu) re-reads every input pixel nine times and the filter bank once
+// per tile; with 128x64 tiles that is 24 KB of L2->SM traffic per 128x64x64 MACs and the SM's L2 port, not the tensor
+// pipe, is the limit (measured 26 % of the bf16 peak, ncu r01).  Here a persistent CTA per SM keeps all nine 64x64
+// filter taps in shared memory (72 KB) and brings each 16x8-pixel output tile's 18x10 halo ONCE (23 KB) with a single
+// 5-D TMA box over the channel-blocked activation layout [N][C/8][H][W][8].  In shared memory the box is
+// [c/8][18][10][8ch]: every run of 8 pixels along w is a contiguous 128-byte UMMA core matrix, so the A operand of tap
+// (r,s) is just the same buffer viewed through a no-swizzle descriptor whose start address is shifted by
+// (r*10 + s) * 16 bytes (SBO = one halo row = 160 B, LBO = one channel group = 2880 B).  36 MMAs (9 taps x 4 k-steps,
+// M=128, N=64, K=16) per tile accumulate into one of two TMEM buffers while the epilogue warps drain the other.
+#include "common.cuh"
+#include "gemm.h"
+#include "umma.cuh"
+#include "../../include/dvins_perception.h"
+
+namespace dv {
+
+namespace {
+constexpr int TH = 16, TW = 8;                      // output tile (pixels) -> M = 128
+constexpr int HH = TH + 2, HW = TW + 2;             // halo tile
+constexpr int CG = 8;                               // channel groups of 8 (C_in = 64)
+constexpr int HALO_BYTES = CG * HH * HW * 16;       // 23040
+constexpr int HALO_STRIDE = 23552;                  // padded to a multiple of 512 B
+constexpr int STAGES = 3;
+constexpr int W_BYTES = 9 * 64 * 128;               // nine [64 x 64] fp16 taps, SWIZZLE_128B rows
+constexpr int OFF_W = 0;
+constexpr int OFF_HALO = W_BYTES;                   // 73728 (1024-aligned)
+constexpr int OFF_BAR = OFF_HALO + STAGES * HALO_STRIDE;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+}  // namespace
+
+struct HaloParams {
+  int H, W, tiles_w, tiles_h, total_tiles;
+  const float* bias;
+  __half* out;
+  int out_blocked, relu, pool;
+};
+
+__global__ void __launch_bounds__(192, 1) conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                const __grid_constant__ CUtensorMap tmW,
+                                                                const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_bar = acc_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, W_BYTES);
+      for (int t = 0; t < 9; ++t) tma_load_2d(smem + OFF_W + t * 8192, &tmW, w_bar, t * 64, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        const int img = tile / tiles_per_img;
+        const int rem = tile - img * tiles_per_img;
+        const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+        mbar_arrive_expect_tx(&full[s], HALO_BYTES);
+        tma_load_5d(smem + OFF_HALO + s * HALO_STRIDE, &tmX, &full[s], 0, tw_i * TW - 1, th_i * TH - 1, 0, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, 64);
+      mbar_wait(w_bar, 0);
+      const uint32_t w_addr = smem_u32(smem + OFF_W);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES, a = it & 1;
+        mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t h_addr = smem_u32(smem + OFF_HALO + s * HALO_STRIDE);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * 64);
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int r = t / 3, sx = t - r * 3;
+          const uint64_t db0 = make_desc_sw128(w_addr + t * 8192);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            // A: channel groups 2kk, 2kk+1 of the halo, rows shifted by tap (r, sx)
+            const uint64_t da = make_desc_noswz(h_addr + (uint32_t)((2 * kk * HH * HW + r * HW + sx) * 16),
+                                                HH * HW * 16, HW * 16);
+            tc_mma_f16(d_tmem, da, db0 + (uint64_t)(kk * 2), idesc, (uint32_t)((t | kk) != 0));
+          }
+        }
+        tc_commit(&empty[s]);
+        tc_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int hl = row >> 3, wl = row & 7;
+    const int Ho = p.pool ? (p.H >> 1) : p.H, Wo = p.pool ? (p.W >> 1) : p.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+      const int h = th_i * TH + hl, w = tw_i * TW + wl;
+      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64);
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(&acc_empty[a]);      // TMEM buffer free: the next tile's MMAs may start
+      bool writer; int ho, wo;
+      if (p.pool) {
+        ho = h >> 1; wo = w >> 1;
+        writer = !(hl & 1) && !(wl & 1) && ho < Ho && wo < Wo;
+      } else {
+        ho = h; wo = w;
+        writer = h < p.H && w < p.W;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t* rr = c ? r1 : r0;
+        __align__(16) __half2 hv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v0 = __uint_as_float(rr[2 * j]) + __ldg(p.bias + c * 32 + 2 * j);
+          float v1 = __uint_as_float(rr[2 * j + 1]) + __ldg(p.bias + c * 32 + 2 * j + 1);
+          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          hv[j] = __floats2half2_rn(v0, v1);
+        }
+        if (p.pool) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            uint32_t u = *reinterpret_cast<uint32_t*>(&hv[j]);
+            uint32_t o = __shfl_xor_sync(0xffffffffu, u, 1);
+            __half2 m = __hmax2(*reinterpret_cast<__half2*>(&u), *reinterpret_cast<__half2*>(&o));
+            u = *reinterpret_cast<uint32_t*>(&m);
+            o = __shfl_xor_sync(0xffffffffu, u, 8);
+            hv[j] = __hmax2(m, *reinterpret_cast<__half2*>(&o));
+          }
+        }
+        if (writer) {
+          const uint4* src = reinterpret_cast<const uint4*>(hv);
+          if (p.out_blocked) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int64_t off = ((((int64_t)img * 8 + c * 4 + g) * Ho + ho) * Wo + wo) * 8;
+              *reinterpret_cast<uint4*>(p.out + off) = src[g];
+            }
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (((int64_t)img * Ho + ho) * Wo + wo) * 64 + c * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dst[g] = src[g];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int g_num_sms = 148;
+
+int conv_halo_init() {
+  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int dev = 0;
+  DV_CUDA_OK(cudaGetDevice(&dev));
+  DV_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  return DV_OK;
+}
+
+int plan_conv3x3_halo64(HaloPlan* pl, const __half* x, int n_cap, int H, int W, const __half* w, const float* bias,
+                        __half* out, int out_blocked, int relu, int pool) {
+  pl->H = H; pl->W = W; pl->n_cap = n_cap;
+  pl->tiles_w = cdiv(W, TW); pl->tiles_h = cdiv(H, TH);
+  pl->bias = bias; pl->out = out; pl->out_blocked = out_blocked; pl->relu = relu; pl->pool = pool;
+  // activations [N][8][H][W][8]
+  const uint64_t dims[5] = {8, (uint64_t)W, (uint64_t)H, 8, (uint64_t)n_cap};
+  const uint64_t strides[4] = {16, (uint64_t)W * 16, (uint64_t)H * W * 16, (uint64_t)8 * H * W * 16};
+  const uint32_t box[5] = {8, HW, HH, CG, 1};
+  int rc = tmap_encode_f16(&pl->tmX, x, 5, dims, strides, box, /*swizzle128=*/false);
+  if (rc) return rc;
+  const uint64_t wd[2] = {576, 64};
+  const uint64_t ws[1] = {576 * 2};
+  const uint32_t wb[2] = {64, 64};
+  return tmap_encode_f16(&pl->tmW, w, 2, wd, ws, wb, /*swizzle128=*/true);
+}
+
+int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st) {
+  if (n_img <= 0) return DV_OK;
+  if (n_img > pl.n_cap) { set_error("launch_conv_halo64: batch exceeds plan capacity"); return DV_ERR_CAPACITY; }
+  HaloParams p;
+  p.H = pl.H; p.W = pl.W; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.total_tiles = n_img * pl.tiles_w * pl.tiles_h;
+  p.bias = pl.bias; p.out = pl.out; p.out_blocked = pl.out_blocked; p.relu = pl.relu; p.pool = pl.pool;
+  const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+  conv3x3_halo64_kernel<<<grid, 192, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
+  DV_CUDA_OK(cudaGetLastError());
+  return DV_OK;
+}
+
+}  // namespace dv

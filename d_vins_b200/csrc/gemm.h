@@ -45,5 +45,24 @@ int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin
 // rows = M (plain) or number of images (conv).
 int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st);
 int gemm_init();      // resolves cuTensorMapEncodeTiled, sets kernel attributes
+int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                    const uint32_t* box, bool swizzle128);
+
+// ---- weights-stationary halo-tile 3x3 convolution, 64 -> 64 channels (conv_halo.cu) -------------------------------
+// Activations in the channel-blocked layout [N][C/8][H][W][8] ("NC/8HWC8"): one TMA box per 16x8-pixel output tile
+// brings the 18x10 halo ONCE; the nine tap operands are views of it (no-swizzle UMMA descriptors with shifted start
+// addresses).  All nine 64x64 filter taps stay resident in shared memory for the CTA's lifetime (persistent kernel).
+struct HaloPlan {
+  CUtensorMap tmX, tmW;
+  int H = 0, W = 0, n_cap = 0, tiles_w = 0, tiles_h = 0;
+  const float* bias = nullptr;
+  __half* out = nullptr;
+  int out_blocked = 1;     // 1: [N][8][Ho][Wo][8]; 0: NHWC [N][Ho][Wo][64]
+  int relu = 1, pool = 0;
+};
+int plan_conv3x3_halo64(HaloPlan* pl, const __half* x_blocked, int n_cap, int H, int W, const __half* w /*[64,576]*/,
+                        const float* bias, __half* out, int out_blocked, int relu, int pool);
+int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st);
+int conv_halo_init();
 
 }  // namespace dv

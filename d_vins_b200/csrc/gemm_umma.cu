@@ -241,6 +241,32 @@ int gemm_init() {
                                   Cfg<64>::SMEM_BYTES));
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg<128>::SMEM_BYTES));
+  return conv_halo_init();
+}
+
+int conv_halo_init();   // conv_halo.cu
+
+// fp16 tiled tensor map with zero OOB fill; swizzle128 selects SWIZZLE_128B (box inner = 128 B) or none.
+int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                    const uint32_t* box, bool swizzle128) {
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
+  if (!g_encode || (reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tmap_encode_f16: driver entry point missing or base not 16-byte aligned");
+    return DV_ERR_INVALID;
+  }
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d) rank %d", (int)r, rank);
+    set_error(b);
+    return DV_ERR_CUDA;
+  }
   return DV_OK;
 }
 

@@ -2,6 +2,8 @@
 // and the HBM-bound post-net as coalesced kernels: softmax-65 + depth-to-space, fused 3-round 9x9 NMS tile kernel,
 // border/threshold/candidate emission, radix-select top-k + bitonic sort, bilinear descriptor sampling + L2.
 // Semantics follow the reference's export/superpoint.py:52-224 and export/ultrapoint.py:101-127 (see oracle/).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "engine.h"
@@ -21,6 +23,8 @@ struct SpNet {
          *a4a = nullptr, *a4b = nullptr, *aPD = nullptr;
   float *logits = nullptr, *dmap = nullptr;             // [B*h8*w8, 80], [B*h8*w8, 256]
   GemmPlan p1b, p2a, p2b, p3a, p3b, p4a, p4b, pPD, pPb, pDb;
+  HaloPlan h1b, h2a, h2b;                               // weights-stationary halo kernels for the 64->64 layers
+  bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
   // post
   float *smap = nullptr, *nms = nullptr;                // [B,H8,W8]
   unsigned long long* cand = nullptr;                   // [B, H8*W8]
@@ -56,6 +60,54 @@ __global__ void k_gray(const uint8_t* __restrict__ img, float* __restrict__ out,
 // 4 pixels x 128 B = 512 contiguous bytes of the NHWC fp16 output.  A block covers 128 x CONV1A_ROWS pixels so the
 // 72 filter taps each thread needs are loaded once per block.
 #define CONV1A_ROWS 8
+// Channel-blocked variant for the halo-tile conv1b (conv_halo.cu): output [B][8][H][W][8]; warp = channel group,
+// lane = pixel, so a warp writes 32 consecutive pixels x 16 B = 512 contiguous bytes.
+__global__ void __launch_bounds__(256) k_conv1a_blocked(const float* __restrict__ gray, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, __half* __restrict__ out,
+                                                        int H, int W) {
+  __shared__ float tile[CONV1A_ROWS + 2][130];
+  const int b = blockIdx.z, y0 = blockIdx.y * CONV1A_ROWS, x0 = blockIdx.x * 128;
+  const float* g = gray + (int64_t)b * H * W;
+  for (int i = threadIdx.x; i < (CONV1A_ROWS + 2) * 130; i += 256) {
+    const int r = i / 130, c = i - r * 130;
+    const int yy = y0 + r - 1, xx = x0 + c - 1;
+    tile[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? g[(int64_t)yy * W + xx] : 0.f;
+  }
+  const int cg = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    br[c] = bias[cg * 8 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = w[(cg * 8 + c) * 9 + t];
+  }
+  __syncthreads();
+  for (int ry = 0; ry < CONV1A_ROWS; ++ry) {
+    const int y = y0 + ry;
+    if (y >= H) break;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int xl = lane + it * 32;
+      const int x = x0 + xl;
+      if (x >= W) continue;
+      float in[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) in[r * 3 + q] = tile[ry + r][xl + q];
+      __align__(16) __half2 hv[4];
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        float a0 = br[c], a1 = br[c + 1];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) { a0 = fmaf(wr[c][t], in[t], a0); a1 = fmaf(wr[c + 1][t], in[t], a1); }
+        hv[c >> 1] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+      }
+      *reinterpret_cast<uint4*>(out + ((((int64_t)b * 8 + cg) * H + y) * W + x) * 8) = *reinterpret_cast<uint4*>(hv);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) k_conv1a(const float* __restrict__ gray, const float* __restrict__ w,
                                                 const float* __restrict__ bias, __half* __restrict__ out, int H,
                                                 int W) {
@@ -486,6 +538,14 @@ int sp_init(Engine* e) {
   auto ep16 = [](__half* out, int ld, const float* bias, int relu, int pool) {
     EpiParams ep; ep.out16 = out; ep.ld16 = ld; ep.bias = bias; ep.relu = relu; ep.pool = pool; return ep;
   };
+  {
+    const char* env = getenv("DV_SP_HALO");
+    s->use_halo = !(env && env[0] == '0');
+  }
+  // halo path: conv1a -> (blocked) -> conv1b+pool -> (blocked) -> conv2a -> (blocked) -> conv2b+pool -> NHWC
+  DV_TRY(plan_conv3x3_halo64(&s->h1b, s->a1a, B, H, W, s->w[0], s->bias[0], s->a1b, 1, 1, 1));
+  DV_TRY(plan_conv3x3_halo64(&s->h2a, s->a1b, B, H2, W2, s->w[1], s->bias[1], s->a2a, 1, 1, 0));
+  DV_TRY(plan_conv3x3_halo64(&s->h2b, s->a2a, B, H2, W2, s->w[2], s->bias[2], s->a2b, 0, 1, 1));
   DV_TRY(plan_conv3x3(&s->p1b, s->a1a, B, H, W, 64, s->w[0], 64, ep16(s->a1b, 64, s->bias[0], 1, 1)));
   DV_TRY(plan_conv3x3(&s->p2a, s->a1b, B, H2, W2, 64, s->w[1], 64, ep16(s->a2a, 64, s->bias[1], 1, 0)));
   DV_TRY(plan_conv3x3(&s->p2b, s->a2a, B, H2, W2, 64, s->w[2], 64, ep16(s->a2b, 64, s->bias[2], 1, 1)));
@@ -504,9 +564,9 @@ int sp_init(Engine* e) {
                                   NMS_RN * (3 * 4 + 2)));
   // debug views
   e->dbg["gray"] = {s->gray, (int64_t)H * W, 0};
-  e->dbg["conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
-  e->dbg["conv1b_pool"] = {s->a1b, (int64_t)H2 * W2 * 64, 1};
-  e->dbg["conv2a"] = {s->a2a, (int64_t)H2 * W2 * 64, 1};
+  e->dbg[s->use_halo ? "conv1a_blocked" : "conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
+  e->dbg[s->use_halo ? "conv1b_pool_blocked" : "conv1b_pool"] = {s->a1b, (int64_t)H2 * W2 * 64, 1};
+  e->dbg[s->use_halo ? "conv2a_blocked" : "conv2a"] = {s->a2a, (int64_t)H2 * W2 * 64, 1};
   e->dbg["conv2b_pool"] = {s->a2b, (int64_t)H4 * W4 * 64, 1};
   e->dbg["conv3a"] = {s->a3a, (int64_t)H4 * W4 * 128, 1};
   e->dbg["conv3b_pool"] = {s->a3b, (int64_t)h8 * w8 * 128, 1};
@@ -532,14 +592,25 @@ int sp_run_encoder(Engine* e, int b) {
   const int H = e->H, W = e->W;
   const int64_t npix = (int64_t)b * H * W;
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
-  k_conv1a<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
-  DV_CUDA_OK(cudaGetLastError());
-  {
-    ProbeScope pr(e);
-    DV_TRY(launch_gemm(s->p1b, b, e->st));
+  if (s->use_halo) {
+    k_conv1a_blocked<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
+    DV_CUDA_OK(cudaGetLastError());
+    {
+      ProbeScope pr(e);
+      DV_TRY(launch_conv_halo64(s->h1b, b, e->st));
+    }
+    DV_TRY(launch_conv_halo64(s->h2a, b, e->st));
+    DV_TRY(launch_conv_halo64(s->h2b, b, e->st));
+  } else {
+    k_conv1a<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
+    DV_CUDA_OK(cudaGetLastError());
+    {
+      ProbeScope pr(e);
+      DV_TRY(launch_gemm(s->p1b, b, e->st));
+    }
+    DV_TRY(launch_gemm(s->p2a, b, e->st));
+    DV_TRY(launch_gemm(s->p2b, b, e->st));
   }
-  DV_TRY(launch_gemm(s->p2a, b, e->st));
-  DV_TRY(launch_gemm(s->p2b, b, e->st));
   DV_TRY(launch_gemm(s->p3a, b, e->st));
   DV_TRY(launch_gemm(s->p3b, b, e->st));
   DV_TRY(launch_gemm(s->p4a, b, e->st));

@@ -168,6 +168,10 @@ dv_status dv_dbg_gemm(dv_engine* e, const float* A, const float* B, const float*
  * layout), y [n,h',w',cout] with h' = pool ? h/2 : h. */
 dv_status dv_dbg_conv3x3(dv_engine* e, const float* x, const float* wgt, const float* bias, int32_t n, int32_t h,
                          int32_t w, int32_t cin, int32_t cout, int32_t relu, int32_t pool, float* y);
+/* Same op through the weights-stationary halo-tile kernel (cin = cout = 64; conv_halo.cu).  x / y are NHWC on the host;
+ * the entry point converts to / from the channel-blocked device layout.  out_blocked selects the device output layout. */
+dv_status dv_dbg_conv3x3_halo64(dv_engine* e, const float* x, const float* wgt, const float* bias, int32_t n, int32_t h,
+                                int32_t w, int32_t relu, int32_t pool, int32_t out_blocked, float* y);
 /* NMS + border + threshold + top-k on a caller-supplied f32 score map [h8,w8] (integer stage in isolation). */
 dv_status dv_dbg_nms_select(dv_engine* e, const float* score_map, int32_t h8, int32_t w8, float* nms_out,
                             int32_t* kpts_xy, float* scores, int32_t* n);

@@ -49,3 +49,24 @@ def test_conv3x3(eng, n, h, w, cin, cout, pool):
     assert y.shape == ref.shape
     err = np.abs(y - ref).max()
     assert err < 4e-3, err     # output stored as fp16 (rel 2^-11 of values up to ~4)
+
+
+@pytest.mark.parametrize("n,h,w,pool,blocked", [(1, 16, 8, False, True), (1, 32, 24, True, True), (2, 48, 40, False, False),
+                                               (1, 37, 29, True, False), (3, 120, 188, True, True), (1, 480, 752, True, True)])
+def test_conv3x3_halo64(eng, n, h, w, pool, blocked):
+    """Weights-stationary halo-tile kernel (conv_halo.cu): one TMA halo box per 16x8 tile, nine shifted no-swizzle views."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(h * w + n)
+    x = rng.standard_normal((n, h, w, 64)).astype(np.float32)
+    wt = (rng.standard_normal((64, 64, 3, 3)) * np.sqrt(2.0 / 576)).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(64)).astype(np.float32)
+    y = eng.dbg_conv3x3_halo64(x, wt, bias, relu=True, pool=pool, out_blocked=blocked)
+    xt = torch.from_numpy(_q(x)).permute(0, 3, 1, 2).double()
+    r = F.relu(F.conv2d(xt, torch.from_numpy(_q(wt)).double(), torch.from_numpy(bias).double(), padding=1))
+    if pool:
+        r = F.max_pool2d(r, 2, 2)
+    ref = r.permute(0, 2, 3, 1).numpy()
+    assert y.shape == ref.shape
+    err = np.abs(y - ref).max()
+    assert err < 4e-3, err
