@@ -28,7 +28,8 @@ constexpr int W_BYTES = 9 * 64 * 128;               // nine [64 x 64] fp16 taps,
 constexpr int OFF_W = 0;
 constexpr int OFF_HALO = W_BYTES;                   // 73728 (1024-aligned)
 constexpr int OFF_BAR = OFF_HALO + STAGES * HALO_STRIDE;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int OFF_BIAS = OFF_BAR + 256;
+constexpr int SMEM_BYTES = OFF_BIAS + 256 + 1024;
 }  // namespace
 
 struct HaloParams {
@@ -38,7 +39,7 @@ struct HaloParams {
   int out_blocked, relu, pool;
 };
 
-__global__ void __launch_bounds__(192, 1) conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                 const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -56,10 +57,12 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo64_kernel(const __grid_con
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
+  float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  if (threadIdx.x >= 64 && threadIdx.x < 128) sbias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
   if (warp == 1) tmem_alloc(tmem_ptr, 128);
   tc_fence_before();
   __syncthreads();
@@ -85,36 +88,38 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo64_kernel(const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16_f32(128, 64);
       mbar_wait(w_bar, 0);
-      const uint32_t w_addr = smem_u32(smem + OFF_W);
+      const uint64_t db_base = make_desc_sw128(smem_u32(smem + OFF_W));
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, a = it & 1;
         mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
         mbar_wait(&full[s], (it / STAGES) & 1);
         tc_fence_after();
-        const uint32_t h_addr = smem_u32(smem + OFF_HALO + s * HALO_STRIDE);
+        // descriptors differ from the per-stage / per-tap bases only in the 14-bit start-address field (addr >> 4)
+        const uint64_t da_base = make_desc_noswz(smem_u32(smem + OFF_HALO + s * HALO_STRIDE), HH * HW * 16, HW * 16);
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * 64);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
           const int r = t / 3, sx = t - r * 3;
-          const uint64_t db0 = make_desc_sw128(w_addr + t * 8192);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            // A: channel groups 2kk, 2kk+1 of the halo, rows shifted by tap (r, sx)
-            const uint64_t da = make_desc_noswz(h_addr + (uint32_t)((2 * kk * HH * HW + r * HW + sx) * 16),
-                                                HH * HW * 16, HW * 16);
-            tc_mma_f16(d_tmem, da, db0 + (uint64_t)(kk * 2), idesc, (uint32_t)((t | kk) != 0));
-          }
+          for (int kk = 0; kk < 4; ++kk)
+            tc_mma_f16(d_tmem, da_base + (uint64_t)(2 * kk * HH * HW + r * HW + sx), db_base + (uint64_t)(t * 512 + kk * 2),
+                       idesc, (uint32_t)((t | kk) != 0));
         }
         tc_commit(&empty[s]);
         tc_commit(&acc_full[a]);
       }
     }
   } else {
+    // 8 epilogue warps: warp w owns TMEM lane quarter (w & 3) and the 32-column half ((w - 2) >> 2)
     const int q = warp & 3;
+    const int c = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
     const int Ho = p.pool ? (p.H >> 1) : p.H, Wo = p.pool ? (p.W >> 1) : p.W;
+    float bv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bv[j] = sbias[c * 32 + j];
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
@@ -124,10 +129,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo64_kernel(const __grid_con
       const int h = th_i * TH + hl, w = tw_i * TW + wl;
       mbar_wait(&acc_full[a], (it >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64);
-      tmem_ld32(taddr, r0);
-      tmem_ld32(taddr + 32, r1);
+      uint32_t rr[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 64 + c * 32), rr);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -140,41 +143,37 @@ __global__ void __launch_bounds__(192, 1) conv3x3_halo64_kernel(const __grid_con
         ho = h; wo = w;
         writer = h < p.H && w < p.W;
       }
+      __align__(16) __half2 hv[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t* rr = c ? r1 : r0;
-        __align__(16) __half2 hv[16];
+      for (int j = 0; j < 16; ++j) {
+        float v0 = __uint_as_float(rr[2 * j]) + bv[2 * j];
+        float v1 = __uint_as_float(rr[2 * j + 1]) + bv[2 * j + 1];
+        if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+        hv[j] = __floats2half2_rn(v0, v1);
+      }
+      if (p.pool) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v0 = __uint_as_float(rr[2 * j]) + __ldg(p.bias + c * 32 + 2 * j);
-          float v1 = __uint_as_float(rr[2 * j + 1]) + __ldg(p.bias + c * 32 + 2 * j + 1);
-          if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-          hv[j] = __floats2half2_rn(v0, v1);
+          uint32_t u = *reinterpret_cast<uint32_t*>(&hv[j]);
+          uint32_t o = __shfl_xor_sync(0xffffffffu, u, 1);
+          __half2 m = __hmax2(*reinterpret_cast<__half2*>(&u), *reinterpret_cast<__half2*>(&o));
+          u = *reinterpret_cast<uint32_t*>(&m);
+          o = __shfl_xor_sync(0xffffffffu, u, 8);
+          hv[j] = __hmax2(m, *reinterpret_cast<__half2*>(&o));
         }
-        if (p.pool) {
+      }
+      if (writer) {
+        const uint4* src = reinterpret_cast<const uint4*>(hv);
+        if (p.out_blocked) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            uint32_t u = *reinterpret_cast<uint32_t*>(&hv[j]);
-            uint32_t o = __shfl_xor_sync(0xffffffffu, u, 1);
-            __half2 m = __hmax2(*reinterpret_cast<__half2*>(&u), *reinterpret_cast<__half2*>(&o));
-            u = *reinterpret_cast<uint32_t*>(&m);
-            o = __shfl_xor_sync(0xffffffffu, u, 8);
-            hv[j] = __hmax2(m, *reinterpret_cast<__half2*>(&o));
+          for (int g = 0; g < 4; ++g) {
+            const int64_t off = ((((int64_t)img * 8 + c * 4 + g) * Ho + ho) * Wo + wo) * 8;
+            *reinterpret_cast<uint4*>(p.out + off) = src[g];
           }
-        }
-        if (writer) {
-          const uint4* src = reinterpret_cast<const uint4*>(hv);
-          if (p.out_blocked) {
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + (((int64_t)img * Ho + ho) * Wo + wo) * 64 + c * 32);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int64_t off = ((((int64_t)img * 8 + c * 4 + g) * Ho + ho) * Wo + wo) * 8;
-              *reinterpret_cast<uint4*>(p.out + off) = src[g];
-            }
-          } else {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (((int64_t)img * Ho + ho) * Wo + wo) * 64 + c * 32);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) dst[g] = src[g];
-          }
+          for (int g = 0; g < 4; ++g) dst[g] = src[g];
         }
       }
     }
@@ -223,7 +222,7 @@ int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st) {
   p.total_tiles = n_img * pl.tiles_w * pl.tiles_h;
   p.bias = pl.bias; p.out = pl.out; p.out_blocked = pl.out_blocked; p.relu = pl.relu; p.pool = pl.pool;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv3x3_halo64_kernel<<<grid, 192, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
+  conv3x3_halo64_kernel<<<grid, 320, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
   DV_CUDA_OK(cudaGetLastError());
   return DV_OK;
 }
