@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(w_bar, W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem + OFF_W + t * 8192, &tmW, w_bar, t * 64, 0);
       int it = 0;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_f16_f32(128, 64);
       mbar_wait(w_bar, 0);
       const uint64_t db_base = make_desc_sw128(smem_u32(smem + OFF_W));

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % C::STAGES;
         const int r = kb / C::STAGES;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % C::STAGES;

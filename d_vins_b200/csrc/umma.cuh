@@ -149,3 +149,18 @@ __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 }  // namespace dv
+
+namespace dv {
+// One lane of a converged warp.  nvcc recognises the elect.sync idiom and keeps the guarded region's address
+// arithmetic on the uniform datapath (with `lane == 0` every tcgen05.mma was preceded by ELECT/R2UR sequences that
+// throttled the issue rate to ~70 cycles per MMA - ncu r01).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+}  // namespace dv
