@@ -129,3 +129,29 @@ def test_rejects_wrong_size(eng):
     from d_vins_b200 import capi
     with pytest.raises(capi.DvError):
         eng.frame_upload(np.zeros((100, 100), np.uint8))
+
+
+def test_kitti_shape_376x1241(weights_file, all_weights):
+    """BASELINE config 5 shape: W not divisible by 8 -> score map 376x1240, pooled widths 620/310/155."""
+    import os
+    from d_vins_b200 import capi
+    from oracle import superpoint as osp, synth, weights
+    e = capi.Engine(height=376, width=1241, weights_path=weights_file)
+    try:
+        img = synth.make_frame(376, 1241, synth.BASE_SEED + 5)
+        o = osp.superpoint(weights.sub(all_weights, "sp."), img)
+        e.frame_upload(img)
+        r = e.sp_detect()
+        sm = e.dbg_read("score_map").reshape(376, 1240)
+        assert np.abs(sm - o["score_map"]).max() < parity.SCORE_ATOL
+        exact, missing, unexplained, rep = parity.check_keypoints(o, r)
+        assert missing == 0 and unexplained == 0 and exact >= 0.9 * len(o["kpts"]), rep
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sp_kitti.npz"))
+        gs = {(int(x), int(y)) for x, y in g["kpts"]}
+        assert len(gs & {(int(x), int(y)) for x, y in r["kpts"]}) >= 0.9 * len(gs)
+        # integer halves: 1241 // 2 = 620
+        assert np.array_equal(r["kpts_norm"], osp.normalize_kpts(r["kpts"], 1241, 376))
+        nms, kp, sc = e.dbg_nms_select(o["score_map"])
+        assert np.array_equal(kp, o["kpts"]) and np.array_equal(nms, o["nms"])
+    finally:
+        e.close()
