@@ -326,9 +326,14 @@ def main():
     tf_peak, hbm_peak, peak_src = _peaks()
     k_ms = probe_ms / max(probe_n, 1)
     achieved = CONV1B_FLOP_PER_FRAME * b / (k_ms * 1e-3) / 1e12 if probe_n else None
-    roofline = {"kernel": "umma_gemm_kernel<64> (conv1b 3x3 64->64 + ReLU + 2x2 max-pool, implicit GEMM, %d frames/launch)" % b,
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 8 frames/launch from the committed
+    # ncu --set full capture (profiles/r01_conv1b_halo_ncu_raw_selected.txt): 369.8 MB + 79.6 MB
+    traffic = (369.773056e6 + 79.608576e6) * b / 8.0
+    roofline = {"kernel": "conv3x3_halo64_kernel (conv1b 3x3 64->64 + ReLU + 2x2 max-pool, halo-tile implicit GEMM, %d frames/launch)" % b,
                 "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                "frac": (achieved / tf_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / tf_peak) if achieved else None, "traffic": traffic,
+                "traffic_source": "ncu --set full, profiles/r01_conv1b_halo_ncu_raw_selected.txt (scaled by batch/8)",
+                "peak_source": peak_src,
                 "avg_launch_ms": k_ms, "launches_timed": probe_n,
                 "flop_per_launch": CONV1B_FLOP_PER_FRAME * b,
                 "whole_frame_tflops": FRAME_GFLOP * value / 1e3}
