@@ -1,0 +1,261 @@
+// Persistent variant of the tcgen05 GEMM / tap-per-TMA implicit-GEMM conv (same operands, same fused epilogue as
+// gemm_umma.cu): one CTA per SM loops over output tiles, so barrier init / TMEM allocation / tensor-map fetch are
+// paid once per SM instead of once per 128 x BN tile, and the accumulator is double-buffered in TMEM so the epilogue
+// of tile i (8 warps) overlaps the TMA + MMA main loop of tile i+1.  Round-1 launch lists showed the one-tile-per-CTA
+// kernel spending 8-17 us on GEMMs whose MMA time is 1-2 us (LightGlue / MixVPR layers): fixed per-CTA cost.
+#include "common.cuh"
+#include "gemm.h"
+#include "umma.cuh"
+#include "../../include/dvins_perception.h"
+
+namespace dv {
+
+template <int BN>
+struct PCfg {
+  static constexpr int STAGES = (BN == 64) ? 8 : 6;
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;          // two accumulators
+};
+
+template <int BN>
+__global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const GemmParams p, const int m_tiles) {
+  using C = PCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* acc_full = empty + C::STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int kc = 0;                                     // running k-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+        int img = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          const int tw_i = m_tile % p.tiles_w;
+          const int t2 = m_tile / p.tiles_w;
+          const int th_i = t2 % p.tiles_h;
+          img = t2 / p.tiles_h;
+          w0 = tw_i << p.tw_log2;
+          h0 = th_i * (128 >> p.tw_log2);
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
+          const int s = kc % C::STAGES;
+          mbar_wait(&empty[s], ((kc / C::STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full[s], C::STAGE_BYTES);
+          uint8_t* sA = smem + s * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          int kB;
+          if (p.conv) {
+            const int tap = kb / p.cin_blocks;
+            const int cb = kb - tap * p.cin_blocks;
+            const int r3 = tap / 3, s3 = tap - r3 * 3;
+            tma_load_4d(sA, &tmA, &full[s], cb * 64, w0 + s3 - 1, h0 + r3 - 1, img);
+            kB = tap * p.cin + cb * 64;
+          } else {
+            tma_load_2d(sA, &tmA, &full[s], kb * 64, m_tile * 128);
+            kB = kb * 64;
+          }
+          tma_load_2d(sB, &tmB, &full[s], kB, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
+      int kc = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++kc) {
+          const int s = kc % C::STAGES;
+          mbar_wait(&full[s], (kc / C::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint64_t da = make_desc_sw128(a_addr);
+          const uint64_t db = make_desc_sw128(a_addr + C::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (uint32_t)((kb | k) != 0));
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 8 warps
+    const int q = warp & 3;                    // TMEM lane quarter
+    const int half = (warp - 2) >> 2;          // this warp takes chunks half, half+2, ...
+    const int row = q * 32 + lane;
+    const EpiParams& ep = p.epi;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+      const int n0 = n_tile * BN;
+      long out_row = -1;
+      bool writer = false;
+      if (p.conv) {
+        const int tw_i = m_tile % p.tiles_w;
+        const int t2 = m_tile / p.tiles_w;
+        const int th_i = t2 % p.tiles_h;
+        const int img = t2 / p.tiles_h;
+        const int TW = 1 << p.tw_log2;
+        const int hl = row >> p.tw_log2, wl = row & (TW - 1);
+        const int h = th_i * (128 >> p.tw_log2) + hl, w = (tw_i << p.tw_log2) + wl;
+        if (ep.pool) {
+          const int Ho = p.H >> 1, Wo = p.W >> 1;
+          writer = !(hl & 1) && !(wl & 1) && (h >> 1) < Ho && (w >> 1) < Wo;
+          out_row = ((long)img * Ho + (h >> 1)) * Wo + (w >> 1);
+        } else {
+          writer = h < p.H && w < p.W;
+          out_row = ((long)img * p.H + h) * p.W + w;
+        }
+      } else {
+        const long g = (long)m_tile * 128 + row;
+        writer = g < p.M;
+        out_row = g;
+      }
+      mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+#pragma unroll 1
+      for (int c = half; c < BN / 32; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;          // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int ncols = min(32, p.N - col0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias) {
+          // one coalesced load per warp, then broadcast: lane j holds bias[col0 + j]
+          const float bl = (lane < ncols) ? __ldg(ep.bias + col0 + lane) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
+        }
+        if (ep.res32 && writer && !ep.pool) {
+          const float4* rp = reinterpret_cast<const float4*>(ep.res32 + out_row * ep.ldr32 + col0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g * 4 + 4 <= ncols) {
+              const float4 t = rp[g];   // plain load: may alias out32 (in-place residual)
+              v[g * 4 + 0] += t.x; v[g * 4 + 1] += t.y; v[g * 4 + 2] += t.z; v[g * 4 + 3] += t.w;
+            }
+        }
+        if (ep.res16 && writer && !ep.pool) {
+          const uint4* rp = reinterpret_cast<const uint4*>(ep.res16 + out_row * ep.ldr16 + col0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g * 8 + 8 <= ncols) {
+              const uint4 t = __ldg(rp + g);
+              const __half2* h2 = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(h2[e]);
+                v[g * 8 + 2 * e] += f.x; v[g * 8 + 2 * e + 1] += f.y;
+              }
+            }
+        }
+        if (ep.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (ep.out32 && writer && !ep.pool) {
+          float4* op = reinterpret_cast<float4*>(ep.out32 + out_row * ep.ld32 + col0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g * 4 + 4 <= ncols) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+        if (ep.out16) {
+          __align__(16) __half2 hv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hv[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          if (ep.pool) {
+            const int TW = 1 << p.tw_log2;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              uint32_t u = *reinterpret_cast<uint32_t*>(&hv[j]);
+              uint32_t o = __shfl_xor_sync(0xffffffffu, u, 1);
+              __half2 m = __hmax2(*reinterpret_cast<__half2*>(&u), *reinterpret_cast<__half2*>(&o));
+              u = *reinterpret_cast<uint32_t*>(&m);
+              o = __shfl_xor_sync(0xffffffffu, u, TW);
+              hv[j] = __hmax2(m, *reinterpret_cast<__half2*>(&o));
+            }
+          }
+          if (writer) {
+            uint4* op = reinterpret_cast<uint4*>(ep.out16 + out_row * ep.ld16 + col0);
+            const uint4* src = reinterpret_cast<const uint4*>(hv);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (g * 8 + 8 <= ncols) op[g] = src[g];
+          }
+        }
+      }
+      // all of this warp's TMEM reads of buffer `a` are complete (tmem_ld_wait above)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(&acc_empty[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+static int g_sms = 148;
+
+int gemm_persistent_init() {
+  DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  PCfg<64>::SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_persist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  PCfg<128>::SMEM_BYTES));
+  int dev = 0;
+  DV_CUDA_OK(cudaGetDevice(&dev));
+  DV_CUDA_OK(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+  return DV_OK;
+}
+
+int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st) {
+  const long total = m_tiles * p.n_tiles;
+  const int grid = (int)(total < g_sms ? total : g_sms);
+  if (pl.bn == 64)
+    umma_gemm_persist_kernel<64><<<grid, 320, PCfg<64>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, p, (int)m_tiles);
+  else
+    umma_gemm_persist_kernel<128><<<grid, 320, PCfg<128>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, p, (int)m_tiles);
+  DV_CUDA_OK(cudaGetLastError());
+  return DV_OK;
+}
+
+}  // namespace dv

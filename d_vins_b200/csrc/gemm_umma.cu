@@ -7,6 +7,8 @@
 // another's main loop.  The 3x3 convolution variant is an implicit GEMM: the A tile of K-block (tap, channel
 // block) is a 4-D TMA box over the NHWC activation tensor shifted by the tap offset; out-of-bounds (including
 // negative) coordinates are zero-filled by the TMA unit, which IS the conv zero padding.
+#include <stdlib.h>
+
 #include "gemm.h"
 #include "umma.cuh"
 #include "common.cuh"
@@ -225,6 +227,9 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_tmapEncodeTiled g_encode = nullptr;
+static bool g_use_persistent = true;
+int gemm_persistent_init();                                                                    // gemm_persistent.cu
+int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
 
 int gemm_init() {
   if (!g_encode) {
@@ -241,6 +246,12 @@ int gemm_init() {
                                   Cfg<64>::SMEM_BYTES));
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   Cfg<128>::SMEM_BYTES));
+  {
+    const char* env = getenv("DV_GEMM_PERSISTENT");      // debug toggle: 0 = one tile per CTA (original kernel)
+    g_use_persistent = !(env && env[0] == '0');
+  }
+  int rc = gemm_persistent_init();
+  if (rc) return rc;
   return conv_halo_init();
 }
 
@@ -375,6 +386,7 @@ int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st) {
     p.M = rows;
     m_tiles = cdiv(rows, 128);
   }
+  if (g_use_persistent) return launch_gemm_persistent(pl, p, m_tiles, st);
   const long grid = m_tiles * p.n_tiles;
   if (pl.bn == 64)
     umma_gemm_kernel<64><<<(unsigned)grid, 192, Cfg<64>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, p);
