@@ -116,7 +116,9 @@ def cpu_pipe(W_all, frames, vio, bank, steps, warmup):
     import torch
     from oracle import weights, superpoint as osp, mixvpr as omix, lightglue as olg, knn
     ws, wl, wm = weights.sub(W_all, "sp."), weights.sub(W_all, "lg."), weights.sub(W_all, "mix.")
-    cores = os.cpu_count() or 1
+    # PyTorch CPU convs at these sizes stop scaling past ~32 threads (measured on the 128-thread B200 host: 0.37 s/frame
+    # SuperPoint at 16-32 threads, 0.61 s at 64, worse at 128), so the baseline uses the fastest setting it can.
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     prev = None
     t0 = None
@@ -166,7 +168,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=8, help="frames per rank per round")
+    ap.add_argument("--batch", type=int, default=32, help="frames per rank per round")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

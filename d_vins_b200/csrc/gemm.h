@@ -18,7 +18,16 @@ struct EpiParams {
   const float* res32 = nullptr; int ldr32 = 0;
   int relu = 0;
   int pool = 0;
+  // rotary embedding fused into the store (LightGlue Wqkv; persistent kernel only): columns [0, rope_cols) are
+  // (2j, 2j+1) pairs rotated by angle j = (col % 64) / 2 of the row: tables [rows, 32] fp32.
+  const float* rope_cs = nullptr;
+  const float* rope_sn = nullptr;
+  int rope_cols = 0;
+  // out16 in the channel-blocked layout [rows / blocked_hw][N/8][blocked_hw][8] (input format of conv_halo.cu);
+  // persistent kernel only, plain (non-conv) mode.  0 = row-major.
+  int blocked_hw = 0;
 };
+bool gemm_is_persistent();
 
 struct GemmParams {
   int M, N, K;          // M rows actually computed (set at launch), N output columns, K reduction length
@@ -27,6 +36,11 @@ struct GemmParams {
   int conv;             // 0: plain row-major A; 1: 3x3 pad-1 conv over NHWC A
   int H, W, cin, cin_blocks, tw_log2, tiles_w, tiles_h;
   EpiParams epi;
+  // batched mode (persistent kernel only): tile -> (batch b, m_tile, n_tile); operands are row windows of the same two
+  // tensors: A rows [batch[b].x, +batch[b].z), B rows [batch[b].y, +batch[b].w); output b at out32 + b * out_bstride.
+  const int4* batch = nullptr;
+  int batch_count = 0, batch_m_tiles = 0;
+  long out_bstride = 0;
 };
 
 struct GemmPlan {
@@ -44,6 +58,9 @@ int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin
                  const EpiParams& epi);
 // rows = M (plain) or number of images (conv).
 int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st);
+// batched: `desc` device array of {a_row_off, b_row_off, m, n}; max_m / max_n bound the tile grid (fp32 output only)
+int launch_gemm_batched(const GemmPlan& pl, const int4* desc, int count, int max_m, int max_n, long out_bstride,
+                        cudaStream_t st);
 int gemm_init();      // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                     const uint32_t* box, bool swizzle128);

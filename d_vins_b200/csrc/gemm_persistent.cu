@@ -21,6 +21,34 @@ struct PCfg {
   static constexpr int TMEM_COLS = 2 * BN;          // two accumulators
 };
 
+struct TileXY {
+  int m_tile, n_tile;     // tile indices inside the (batch) problem
+  int a_row, b_row;       // first A / B row of the problem (batched mode), else 0
+  int m_lim, n_lim;       // rows / columns of the problem
+  long out_off;           // element offset of the problem's output
+  bool valid;
+};
+template <int BN>
+__device__ __forceinline__ TileXY decode_tile(const GemmParams& p, int tile) {
+  TileXY t;
+  if (p.batch) {
+    const int per = p.batch_m_tiles * p.n_tiles;
+    const int b = tile / per;
+    const int rem = tile - b * per;
+    t.m_tile = rem / p.n_tiles;
+    t.n_tile = rem - t.m_tile * p.n_tiles;
+    const int4 d = __ldg(p.batch + b);
+    t.a_row = d.x; t.b_row = d.y; t.m_lim = d.z; t.n_lim = (d.w + 3) & ~3;
+    t.out_off = (long)b * p.out_bstride;
+    t.valid = t.m_tile * 128 < d.z && t.n_tile * BN < d.w;
+  } else {
+    t.n_tile = tile % p.n_tiles;
+    t.m_tile = tile / p.n_tiles;
+    t.a_row = 0; t.b_row = 0; t.m_lim = p.M; t.n_lim = p.N; t.out_off = 0; t.valid = true;
+  }
+  return t;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
@@ -53,7 +81,9 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
     if (elect_one_sync()) {
       int kc = 0;                                     // running k-block counter across tiles (ring position)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+        const TileXY tx = decode_tile<BN>(p, tile);
+        if (!tx.valid) continue;
+        const int n_tile = tx.n_tile, m_tile = tx.m_tile;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
           const int tw_i = m_tile % p.tiles_w;
@@ -77,10 +107,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
             tma_load_4d(sA, &tmA, &full[s], cb * 64, w0 + s3 - 1, h0 + r3 - 1, img);
             kB = tap * p.cin + cb * 64;
           } else {
-            tma_load_2d(sA, &tmA, &full[s], kb * 64, m_tile * 128);
+            tma_load_2d(sA, &tmA, &full[s], kb * 64, tx.a_row + m_tile * 128);
             kB = kb * 64;
           }
-          tma_load_2d(sB, &tmB, &full[s], kB, n_tile * BN);
+          tma_load_2d(sB, &tmB, &full[s], kB, tx.b_row + n_tile * BN);
         }
       }
     }
@@ -88,7 +118,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
     if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_f16_f32(128, BN);
       int kc = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (!decode_tile<BN>(p, tile).valid) continue;
         const int a = it & 1;
         mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -106,6 +137,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[a]);
+        ++it;
       }
     }
   } else {
@@ -115,10 +147,13 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
     const int row = q * 32 + lane;
     const EpiParams& ep = p.epi;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileXY tx = decode_tile<BN>(p, tile);
+      if (!tx.valid) continue;
       const int a = it & 1;
-      const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+      const int n_tile = tx.n_tile, m_tile = tx.m_tile;
       const int n0 = n_tile * BN;
+      const int Nlim = tx.n_lim;
       long out_row = -1;
       bool writer = false;
       if (p.conv) {
@@ -139,7 +174,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
         }
       } else {
         const long g = (long)m_tile * 128 + row;
-        writer = g < p.M;
+        writer = g < tx.m_lim;
         out_row = g;
       }
       mbar_wait(&acc_full[a], (it >> 1) & 1);
@@ -148,11 +183,11 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;          // warp-uniform
+        if (col0 >= Nlim) break;         // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        const int ncols = min(32, p.N - col0);
+        const int ncols = min(32, Nlim - col0);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -189,8 +224,25 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
+        if (ep.rope_cs && col0 < ep.rope_cols && writer) {      // warp-uniform except `writer`
+          const int j0 = (col0 & 63) >> 1;
+          const float4* cp = reinterpret_cast<const float4*>(ep.rope_cs + out_row * 32 + j0);
+          const float4* sp = reinterpret_cast<const float4*>(ep.rope_sn + out_row * 32 + j0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 c4 = __ldg(cp + g), s4 = __ldg(sp + g);
+            const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int jj = g * 4 + e;
+              const float x0 = v[2 * jj], x1 = v[2 * jj + 1];
+              v[2 * jj] = x0 * cc[e] - x1 * ss[e];
+              v[2 * jj + 1] = x1 * cc[e] + x0 * ss[e];
+            }
+          }
+        }
         if (ep.out32 && writer && !ep.pool) {
-          float4* op = reinterpret_cast<float4*>(ep.out32 + out_row * ep.ld32 + col0);
+          float4* op = reinterpret_cast<float4*>(ep.out32 + tx.out_off + out_row * ep.ld32 + col0);
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             if (g * 4 + 4 <= ncols) op[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
@@ -212,11 +264,20 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
             }
           }
           if (writer) {
-            uint4* op = reinterpret_cast<uint4*>(ep.out16 + out_row * ep.ld16 + col0);
             const uint4* src = reinterpret_cast<const uint4*>(hv);
+            if (ep.blocked_hw) {
+              const long img = out_row / ep.blocked_hw, pix = out_row - img * ep.blocked_hw;
+              const int ngrp = p.N >> 3;
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if (g * 8 + 8 <= ncols) op[g] = src[g];
+              for (int g = 0; g < 4; ++g)
+                if (g * 8 + 8 <= ncols)
+                  *reinterpret_cast<uint4*>(ep.out16 + ((img * ngrp + (col0 >> 3) + g) * ep.blocked_hw + pix) * 8) = src[g];
+            } else {
+              uint4* op = reinterpret_cast<uint4*>(ep.out16 + out_row * ep.ld16 + col0);
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if (g * 8 + 8 <= ncols) op[g] = src[g];
+            }
           }
         }
       }
@@ -224,6 +285,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(&acc_empty[a]);
+      ++it;
     }
   }
   tc_fence_before();
@@ -256,6 +318,20 @@ int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles
     umma_gemm_persist_kernel<128><<<grid, 320, PCfg<128>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, p, (int)m_tiles);
   DV_CUDA_OK(cudaGetLastError());
   return DV_OK;
+}
+
+int launch_gemm_batched(const GemmPlan& pl, const int4* desc, int count, int max_m, int max_n, long out_bstride,
+                        cudaStream_t st) {
+  if (count <= 0) return DV_OK;
+  GemmParams p = pl.p;
+  if (p.conv || !p.epi.out32 || p.epi.out16 || p.epi.res32 || p.epi.res16) {
+    set_error("launch_gemm_batched: plain fp32-output plans only");
+    return DV_ERR_INVALID;
+  }
+  p.batch = desc; p.batch_count = count; p.out_bstride = out_bstride;
+  p.batch_m_tiles = cdiv(max_m, 128);
+  p.n_tiles = cdiv(max_n, pl.bn);
+  return launch_gemm_persistent(pl, p, (long)count * p.batch_m_tiles, st);
 }
 
 }  // namespace dv

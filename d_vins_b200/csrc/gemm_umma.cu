@@ -228,6 +228,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_tmapEncodeTiled g_encode = nullptr;
 static bool g_use_persistent = true;
+bool gemm_is_persistent() { return g_use_persistent; }
 int gemm_persistent_init();                                                                    // gemm_persistent.cu
 int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
 

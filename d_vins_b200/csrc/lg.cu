@@ -33,13 +33,13 @@ struct LgNet {
   LgLayer L[LG_LAYERS];
   __half* wfinal = nullptr; float* bfinal = nullptr;   // pre-scaled by 256^-1/4
   float *wmatch = nullptr, *bmatch = nullptr;
-  GemmPlan p_final;
+  GemmPlan p_final, p_sim;
   // activations
   __half* X2 = nullptr;                // [T,512]: x (fp16 copy) | msg
   float* x32 = nullptr;                // [T,256] residual stream (fp32 master)
   __half* qkv = nullptr;               // [T,768]
   __half* ctx = nullptr;               // [T,256]
-  float* ffh = nullptr;                // [T,512]
+  __half* ffh = nullptr;               // [T,512] FFN pre-LayerNorm activations (fp16)
   __half* ffg = nullptr;               // [T,512]
   float *cs = nullptr, *sn = nullptr;  // [T,32] rotary cos / sin
   __half* md = nullptr;                // [T,256]
@@ -286,17 +286,19 @@ __global__ void __launch_bounds__(128) k_lg_attention(const AttnJob* __restrict_
 }
 
 // LayerNorm(512, eps 1e-5, affine) + exact (erf) GELU, fp32 in -> fp16 out.  One warp per token.
-__global__ void k_lg_ln_gelu(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+__global__ void k_lg_ln_gelu(const __half* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                              __half* __restrict__ out, int64_t T) {
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + t * 512);
+  const uint2* xr = reinterpret_cast<const uint2*>(x + t * 512);
   float v[16];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float4 a = xr[c * 32 + lane];
-    v[c * 4] = a.x; v[c * 4 + 1] = a.y; v[c * 4 + 2] = a.z; v[c * 4 + 3] = a.w;
+    const uint2 a = xr[c * 32 + lane];
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    v[c * 4] = lo.x; v[c * 4 + 1] = lo.y; v[c * 4 + 2] = hi.x; v[c * 4 + 3] = hi.y;
   }
   float s = 0.f;
 #pragma unroll
@@ -605,16 +607,16 @@ int lg_init(Engine* e) {
     DV_TRY(get_lin(e, pc + "ffn.3", 256, 512, &w, &b));
     DV_TRY(e->upload_f16(w->data, &L.cf3)); DV_TRY(e->upload_f32(b->data, &L.bcf3));
     // plans (A operands are fixed buffers; rows are set at launch)
-    DV_TRY(plan_gemm(&L.p_qkv, g->X2, 512, T, L.wqkv, 256, 768, 256, ep16(g->qkv, 768, L.bqkv)));
+    { EpiParams ep = ep16(g->qkv, 768, L.bqkv);
+      if (gemm_is_persistent()) { ep.rope_cs = g->cs; ep.rope_sn = g->sn; ep.rope_cols = 512; }   // rotary fused into the store
+      DV_TRY(plan_gemm(&L.p_qkv, g->X2, 512, T, L.wqkv, 256, 768, 256, ep)); }
     DV_TRY(plan_gemm(&L.p_out, g->ctx, 256, T, L.wout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bout)));
-    { EpiParams ep; ep.out32 = g->ffh; ep.ld32 = 512; ep.bias = L.bf0;
-      DV_TRY(plan_gemm(&L.p_f0, g->X2, 512, T, L.wf0, 512, 512, 512, ep)); }
+    DV_TRY(plan_gemm(&L.p_f0, g->X2, 512, T, L.wf0, 512, 512, 512, ep16(g->ffh, 512, L.bf0)));
     { EpiParams ep; ep.out32 = g->x32; ep.ld32 = 256; ep.res32 = g->x32; ep.ldr32 = 256; ep.out16 = g->X2; ep.ld16 = 512; ep.bias = L.bf3;
       DV_TRY(plan_gemm(&L.p_f3, g->ffg, 512, T, L.wf3, 512, 256, 512, ep)); }
     DV_TRY(plan_gemm(&L.pc_qkv, g->X2, 512, T, L.cqkv, 256, 512, 256, ep16(g->qkv, 768, L.bcqkv)));
     DV_TRY(plan_gemm(&L.pc_out, g->ctx, 256, T, L.cout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bcout)));
-    { EpiParams ep; ep.out32 = g->ffh; ep.ld32 = 512; ep.bias = L.bcf0;
-      DV_TRY(plan_gemm(&L.pc_f0, g->X2, 512, T, L.cf0, 512, 512, 512, ep)); }
+    DV_TRY(plan_gemm(&L.pc_f0, g->X2, 512, T, L.cf0, 512, 512, 512, ep16(g->ffh, 512, L.bcf0)));
     { EpiParams ep; ep.out32 = g->x32; ep.ld32 = 256; ep.res32 = g->x32; ep.ldr32 = 256; ep.out16 = g->X2; ep.ld16 = 512; ep.bias = L.bcf3;
       DV_TRY(plan_gemm(&L.pc_f3, g->ffg, 512, T, L.cf3, 512, 256, 512, ep)); }
   }
@@ -627,6 +629,9 @@ int lg_init(Engine* e) {
     for (auto& v : bp) v *= 0.25f;
     DV_TRY(e->upload_f16(wp, &g->wfinal)); DV_TRY(e->upload_f32(bp, &g->bfinal));
     DV_TRY(plan_gemm(&g->p_final, g->X2, 512, T, g->wfinal, 256, 256, 256, ep16(g->md, 256, g->bfinal)));
+    { EpiParams es; es.out32 = g->sim; es.ld32 = SC;
+      // B = md too: its tensor map must span all T packed rows (the per-pair window is selected by row offsets)
+      DV_TRY(plan_gemm(&g->p_sim, g->md, 256, T, g->md, 256, T, 256, es)); }
     const HostTensor *wm, *bm;
     DV_TRY(get_lin(e, pa + "matchability", 1, 256, &wm, &bm));
     DV_TRY(e->upload_f32(wm->data, &g->wmatch)); DV_TRY(e->upload_f32(bm->data, &g->bmatch));
@@ -705,7 +710,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     LgLayer& L = g->L[i];
     // self block
     DV_TRY(launch_gemm(L.p_qkv, T, e->st));
-    k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
+    if (!gemm_is_persistent())
+      k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
     k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_self, 0.125f);
     DV_TRY(launch_gemm(L.p_out, T, e->st));
     DV_TRY(launch_gemm(L.p_f0, T, e->st));
@@ -724,14 +730,9 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
   DV_TRY(launch_gemm(g->p_final, T, e->st));
   k_lg_matchability<<<cdiv(T, 8), 256, 0, e->st>>>(g->x32, g->wmatch, g->bmatch, g->z, T);
   DV_LAUNCHED(e, 2);
-  for (int p = 0; p < P; ++p) {   // sim = md0 md1^T : per-pair tensor maps (segment offsets are per call)
-    EpiParams ep; ep.out32 = g->sim + (int64_t)p * SC * SC; ep.ld32 = SC;
-    GemmPlan pl;
-    const int n_pad = std::min((hp[p].n + 7) & ~7, SC);
-    DV_TRY(plan_gemm(&pl, g->md + (int64_t)hp[p].off0 * 256, 256, hp[p].m, g->md + (int64_t)hp[p].off1 * 256, 256, n_pad, 256, ep));
-    DV_TRY(launch_gemm(pl, hp[p].m, e->st));
-    DV_LAUNCHED(e, 1);
-  }
+  // sim_p = md0_p md1_p^T for all pairs in ONE batched launch: operands are row windows of the packed md buffer
+  DV_TRY(launch_gemm_batched(g->p_sim, reinterpret_cast<const int4*>(d_pd), P, max_m, max_n, (long)SC * SC, e->st));
+  DV_LAUNCHED(e, 1);
   return lg_tail(e, P, d_pd, g->d_segs, max_m, max_n, 1);
 }
 

@@ -28,6 +28,7 @@ struct MixNet {
   float* y32 = nullptr;         // [B*400, 256]
   float* gdesc = nullptr;       // [B, 512]
   std::vector<GemmPlan> plans;
+  std::vector<HaloPlan> hplans;        // layer1's 64->64 3x3 convs run on the weights-stationary halo kernel
   std::vector<std::function<int(Engine*, int)>> ops;
   int n_launch = 0;
 };
@@ -325,6 +326,7 @@ int mix_init(Engine* e) {
   DV_TRY(e->alloc(&m->y32, (size_t)B * 400 * 256));
   DV_TRY(e->alloc(&m->gdesc, (size_t)B * 512));
   m->plans.reserve(128);
+  m->hplans.reserve(8);
 
   auto add_w = [&](const std::vector<float>& w, const std::vector<float>& b, __half** dw, float** db) -> int {
     DV_TRY(e->upload_f16(w, dw));
@@ -403,9 +405,20 @@ int mix_init(Engine* e) {
       DV_TRY(add_w(repack_khwc(f2.w, planes, planes, 3, 3, 9 * planes), f2.b, &w2, &b2));
       DV_TRY(add_w(f3.w, f3.b, &w3, &b3));
       // conv1 1x1 + ReLU
-      DV_TRY(add_gemm(x, inpl, B * rows_in, w1, inpl, planes, inpl, epi16(m->t1, planes, b1, 1), rows_in));
+      const bool halo = gemm_is_persistent() && planes == 64 && stride == 1;
+      {
+        EpiParams e1 = epi16(m->t1, planes, b1, 1);
+        if (halo) e1.blocked_hw = rows_in;            // channel-blocked output feeds the halo-tile 3x3
+        DV_TRY(add_gemm(x, inpl, B * rows_in, w1, inpl, planes, inpl, e1, rows_in));
+      }
       // conv2 3x3 (+stride) + ReLU
-      if (stride == 1) {
+      if (halo) {
+        m->hplans.emplace_back();
+        DV_TRY(plan_conv3x3_halo64(&m->hplans.back(), m->t1, B, Hin, Hin, w2, b2, m->t2, /*out_blocked=*/0, 1, 0));
+        const int hidx = (int)m->hplans.size() - 1;
+        m->ops.push_back([hidx](Engine* en, int b) { return launch_conv_halo64(en->mix->hplans[hidx], b, en->st); });
+        m->n_launch++;
+      } else if (stride == 1) {
         DV_TRY(add_conv(m->t1, Hin, Hin, planes, w2, planes, epi16(m->t2, planes, b2, 1)));
       } else {
         const int C = planes, Hi = Hin, Ho = Hout;
