@@ -5,6 +5,7 @@
 // the assignment head (double log-softmax + matchability, mutual arg-max, ordered compaction) is a set of
 // coalesced warp-shuffle kernels.  Architecture restated from cvg/LightGlue (un-vendored; see oracle/lightglue.py).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -25,10 +26,13 @@ struct LgLayer {
   float *bqkv, *bout, *bf0, *bf3, *bcqkv, *bcout, *bcf0, *bcf3;
   float *ln_g, *ln_b, *cln_g, *cln_b;
   GemmPlan p_qkv, p_out, p_f0, p_f3, pc_qkv, pc_out, pc_f0, pc_f3;
+  FfnPlan ffn_s, ffn_c;     // fused FFN blocks (lg_ffn.cu)
 };
 
 struct LgNet {
   int P = 1, segcap = 1024, Tcap = 0;
+  bool fused_ffn = false;              // DV_LG_FUSED_FFN=1: single-kernel FFN (lg_ffn.cu; correct, but weight re-streaming
+                                       // per 128-row block makes it no faster than the 3-kernel path yet - r01 notes)
   float* Wr = nullptr;                 // [32,2]
   LgLayer L[LG_LAYERS];
   __half* wfinal = nullptr; float* bfinal = nullptr;   // pre-scaled by 256^-1/4
@@ -519,6 +523,8 @@ int lg_init(Engine* e) {
   g->P = e->B;
   g->segcap = (e->cfg.lg_max_kpts + 127) & ~127;
   g->Tcap = g->P * 2 * g->segcap;
+  { const char* env = getenv("DV_LG_FUSED_FFN"); g->fused_ffn = (env && env[0] == '1'); }
+  DV_TRY(lg_ffn_init());
   const int T = g->Tcap, P = g->P, SC = g->segcap;
   {
     const HostTensor* wr = e->weight("lg.posenc.Wr.weight");
@@ -614,6 +620,8 @@ int lg_init(Engine* e) {
     DV_TRY(plan_gemm(&L.p_f0, g->X2, 512, T, L.wf0, 512, 512, 512, ep16(g->ffh, 512, L.bf0)));
     { EpiParams ep; ep.out32 = g->x32; ep.ld32 = 256; ep.res32 = g->x32; ep.ldr32 = 256; ep.out16 = g->X2; ep.ld16 = 512; ep.bias = L.bf3;
       DV_TRY(plan_gemm(&L.p_f3, g->ffg, 512, T, L.wf3, 512, 256, 512, ep)); }
+    DV_TRY(plan_lg_ffn(&L.ffn_s, g->X2, T, L.wf0, L.wf3, L.bf0, L.ln_g, L.ln_b, L.bf3, g->x32, g->X2, 512));
+    DV_TRY(plan_lg_ffn(&L.ffn_c, g->X2, T, L.cf0, L.cf3, L.bcf0, L.cln_g, L.cln_b, L.bcf3, g->x32, g->X2, 512));
     DV_TRY(plan_gemm(&L.pc_qkv, g->X2, 512, T, L.cqkv, 256, 512, 256, ep16(g->qkv, 768, L.bcqkv)));
     DV_TRY(plan_gemm(&L.pc_out, g->ctx, 256, T, L.cout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bcout)));
     DV_TRY(plan_gemm(&L.pc_f0, g->X2, 512, T, L.cf0, 512, 512, 512, ep16(g->ffh, 512, L.bcf0)));
@@ -714,16 +722,24 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
       k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
     k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_self, 0.125f);
     DV_TRY(launch_gemm(L.p_out, T, e->st));
-    DV_TRY(launch_gemm(L.p_f0, T, e->st));
-    k_lg_ln_gelu<<<cdiv(T, 8), 256, 0, e->st>>>(g->ffh, L.ln_g, L.ln_b, g->ffg, T);
-    DV_TRY(launch_gemm(L.p_f3, T, e->st));
+    if (g->fused_ffn) {
+      DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
+    } else {
+      DV_TRY(launch_gemm(L.p_f0, T, e->st));
+      k_lg_ln_gelu<<<cdiv(T, 8), 256, 0, e->st>>>(g->ffh, L.ln_g, L.ln_b, g->ffg, T);
+      DV_TRY(launch_gemm(L.p_f3, T, e->st));
+    }
     // cross block
     DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
     k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_cross, 0.125f);
     DV_TRY(launch_gemm(L.pc_out, T, e->st));
-    DV_TRY(launch_gemm(L.pc_f0, T, e->st));
-    k_lg_ln_gelu<<<cdiv(T, 8), 256, 0, e->st>>>(g->ffh, L.cln_g, L.cln_b, g->ffg, T);
-    DV_TRY(launch_gemm(L.pc_f3, T, e->st));
+    if (g->fused_ffn) {
+      DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
+    } else {
+      DV_TRY(launch_gemm(L.pc_f0, T, e->st));
+      k_lg_ln_gelu<<<cdiv(T, 8), 256, 0, e->st>>>(g->ffh, L.cln_g, L.cln_b, g->ffg, T);
+      DV_TRY(launch_gemm(L.pc_f3, T, e->st));
+    }
     DV_LAUNCHED(e, 13);
   }
   DV_CUDA_OK(cudaGetLastError());
