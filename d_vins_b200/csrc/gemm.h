@@ -41,6 +41,8 @@ struct GemmParams {
   const int4* batch = nullptr;
   int batch_count = 0, batch_m_tiles = 0;
   long out_bstride = 0;
+  long long* dbg = nullptr;   // DV_GEMM_DBG=1: epilogue cycle counters of CTA 0 (diagnostics only)
+  int dbg_mode = 0;           // diagnostics: 1 skip global stores, 2 skip bias broadcast, 4 skip TMEM loads
 };
 
 struct GemmPlan {

@@ -3,6 +3,9 @@
 // paid once per SM instead of once per 128 x BN tile, and the accumulator is double-buffered in TMEM so the epilogue
 // of tile i (8 warps) overlaps the TMA + MMA main loop of tile i+1.  Round-1 launch lists showed the one-tile-per-CTA
 // kernel spending 8-17 us on GEMMs whose MMA time is 1-2 us (LightGlue / MixVPR layers): fixed per-CTA cost.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.h"
 #include "umma.cuh"
@@ -17,7 +20,8 @@ struct PCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFF + 512 + 1024;
+  static constexpr int BIAS_OFF = BAR_OFF + 512;                // whole bias vector (N <= 2048 fp32), loaded once per CTA
+  static constexpr int SMEM_BYTES = BIAS_OFF + 8192 + 1024;
   static constexpr int TMEM_COLS = 2 * BN;          // two accumulators
 };
 
@@ -71,6 +75,12 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
     fence_barrier_init();
   }
+  // dbg counters (r01): broadcasting the bias with 32 shuffles per 32-column chunk cost ~1500 cycles per 128x128 tile;
+  // the vector is staged in shared memory once and read back as 128-bit broadcasts.
+  float* sbias = reinterpret_cast<float*>(smem + C::BIAS_OFF);
+  const bool bias_smem = p.epi.bias != nullptr && p.N <= 2048 && !p.batch;
+  if (bias_smem)
+    for (int i = threadIdx.x; i < ((p.N + 127) & ~127); i += blockDim.x) sbias[i] = i < p.N ? p.epi.bias[i] : 0.f;
   if (warp == 1) tmem_alloc(tmem_ptr, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -177,7 +187,17 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
         writer = g < tx.m_lim;
         out_row = g;
       }
+      // bias of this warp's chunks is fetched BEFORE waiting for the accumulator: its (loaded-system) latency would
+      // otherwise be exposed once per chunk on the epilogue's critical path
+      float blv[BN / 64];
+#pragma unroll
+      for (int ci = 0; ci < BN / 64; ++ci) {
+        const int cc = n0 + (half + 2 * ci) * 32 + lane;
+        blv[ci] = (ep.bias && !bias_smem && cc < Nlim) ? __ldg(ep.bias + cc) : 0.f;
+      }
+      const long long te0 = p.dbg ? clock64() : 0;
       mbar_wait(&acc_full[a], (it >> 1) & 1);
+      const long long te1 = p.dbg ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
 #pragma unroll 1
@@ -185,15 +205,26 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
         const int col0 = n0 + c * 32;
         if (col0 >= Nlim) break;         // warp-uniform
         uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
+        if (p.dbg_mode & 4) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0;
+        } else {
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+        }
         const int ncols = min(32, Nlim - col0);
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (ep.bias) {
-          // one coalesced load per warp, then broadcast: lane j holds bias[col0 + j]
-          const float bl = (lane < ncols) ? __ldg(ep.bias + col0 + lane) : 0.f;
+        if (bias_smem) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&sbias[col0 + g * 4]);   // same address in all lanes
+            v[g * 4] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+          }
+        } else if (ep.bias && !(p.dbg_mode & 2)) {
+          // lane j holds bias[col0 + j] (prefetched above); broadcast to every row-owning lane
+          const float bl = blv[(c - half) >> 1];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bl, j);
         }
@@ -241,7 +272,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
             }
           }
         }
-        if (ep.out32 && writer && !ep.pool) {
+        if (ep.out32 && writer && !ep.pool && !(p.dbg_mode & 1)) {
           float4* op = reinterpret_cast<float4*>(ep.out32 + tx.out_off + out_row * ep.ld32 + col0);
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -285,6 +316,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(&acc_empty[a]);
+      if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) { p.dbg[3] += te1 - te0; p.dbg[4] += clock64() - te1; p.dbg[5] += 1; }
       ++it;
     }
   }
@@ -312,11 +344,33 @@ int gemm_persistent_init() {
 int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st) {
   const long total = m_tiles * p.n_tiles;
   const int grid = (int)(total < g_sms ? total : g_sms);
+  static long long* d_dbg = nullptr;
+  static const bool want_dbg = getenv("DV_GEMM_DBG") != nullptr;     // diagnostics: epilogue cycle counters of CTA 0
+  GemmParams pp = p;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (want_dbg) {
+    if (!d_dbg) cudaMalloc(&d_dbg, 64);
+    cudaMemsetAsync(d_dbg, 0, 64, st);
+    pp.dbg = d_dbg;
+    pp.dbg_mode = atoi(getenv("DV_GEMM_DBG"));
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
+  }
   if (pl.bn == 64)
-    umma_gemm_persist_kernel<64><<<grid, 320, PCfg<64>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, p, (int)m_tiles);
+    umma_gemm_persist_kernel<64><<<grid, 320, PCfg<64>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pp, (int)m_tiles);
   else
-    umma_gemm_persist_kernel<128><<<grid, 320, PCfg<128>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, p, (int)m_tiles);
+    umma_gemm_persist_kernel<128><<<grid, 320, PCfg<128>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pp, (int)m_tiles);
   DV_CUDA_OK(cudaGetLastError());
+  if (want_dbg) {
+    long long h[8];
+    float ms = 0.f;
+    cudaEventRecord(e1, st);
+    cudaStreamSynchronize(st);
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[gemm dbg] m_tiles %ld n_tiles %d kb %d bn %d grid %d: %.1f us | CTA0 epilogue: wait %lld work %lld tiles %lld\n",
+            m_tiles, p.n_tiles, p.num_kb, pl.bn, grid, ms * 1e3, h[3], h[4], h[5]);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   return DV_OK;
 }
 
