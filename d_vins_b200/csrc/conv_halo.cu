@@ -29,7 +29,10 @@ constexpr int OFF_W = 0;
 constexpr int OFF_HALO = W_BYTES;                   // 73728 (1024-aligned)
 constexpr int OFF_BAR = OFF_HALO + STAGES * HALO_STRIDE;
 constexpr int OFF_BIAS = OFF_BAR + 256;
-constexpr int SMEM_BYTES = OFF_BIAS + 256 + 1024;
+constexpr int OFF_GRAY = OFF_BIAS + 256;            // FUSE1A: two (TH+4) x (TW+4) fp32 windows of the gray frame
+constexpr int GRAY_H = TH + 4, GRAY_W = TW + 4;
+constexpr int SMEM_BYTES = OFF_GRAY + 2 * GRAY_H * GRAY_W * 4 + 1024;
+constexpr int NPROD = 8;                            // FUSE1A producer warps (one per output channel group of conv1a)
 }  // namespace
 
 struct HaloParams {
@@ -37,11 +40,21 @@ struct HaloParams {
   const float* bias;
   __half* out;
   int out_blocked, relu, pool;
+  // FUSE1A: conv1a (1 -> 64, 3x3, ReLU) is evaluated by the producer warps straight into the halo buffer
+  const float* gray;   // [N, H, W] fp32
+  const float* w1a;    // [64, 9]
+  const float* b1a;    // [64]
 };
 
-__global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                const __grid_constant__ CUtensorMap tmW,
-                                                                const HaloParams p) {
+// FUSE1A = true: SuperPoint conv1a + conv1b in one kernel.  The 64-channel full-resolution conv1a activation (46 MB per
+// 480x752 frame, written and re-read through HBM by the two-kernel version) never exists in memory: eight producer
+// warps (one per group of 8 output channels, lanes = halo pixels) compute the 18x10x64 halo of conv1a on CUDA cores
+// from a 20x12 window of the gray frame and store it as fp16 in exactly the [c/8][18][10][8] layout the TMA box
+// would have produced; pixels outside the image are zeros (conv1b's zero padding), not conv1a evaluated out of range.
+template <bool FUSE1A>
+__global__ void __launch_bounds__(FUSE1A ? 320 + 32 * NPROD : 320, 1)
+conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                      const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -56,7 +69,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_con
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], FUSE1A ? NPROD : 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -74,6 +87,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_con
       mbar_arrive_expect_tx(w_bar, W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem + OFF_W + t * 8192, &tmW, w_bar, t * 64, 0);
       int it = 0;
+      if (!FUSE1A)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES;
         mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -109,6 +123,61 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_con
         tc_commit(&empty[s]);
         tc_commit(&acc_full[a]);
       }
+    }
+  } else if (FUSE1A && warp >= 10) {
+    // ------------------------------------------------------------------ conv1a producers (CUDA cores)
+    const int cg = warp - 10;                       // output channel group of conv1a owned by this warp
+    const int pt = threadIdx.x - 320;               // 0..255 among the producer threads
+    float wr[8][9], br[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      br[c] = p.b1a[cg * 8 + c];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wr[c][t] = p.w1a[(cg * 8 + c) * 9 + t];
+    }
+    float* gbuf = reinterpret_cast<float*>(smem + OFF_GRAY);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES;
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+      const int h0 = th_i * TH - 2, w0 = tw_i * TW - 2;            // top-left of the gray window
+      float* g = gbuf + (it & 1) * (GRAY_H * GRAY_W);
+      if (pt < GRAY_H * GRAY_W) {
+        const int gy = pt / GRAY_W, gx = pt - gy * GRAY_W;
+        const int y = h0 + gy, x = w0 + gx;
+        g[pt] = (y >= 0 && y < p.H && x >= 0 && x < p.W) ? __ldg(p.gray + ((int64_t)img * p.H + y) * p.W + x) : 0.f;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");                // window visible to all producer warps
+      mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);                // the MMAs that read this halo slot have retired
+      uint8_t* halo = smem + OFF_HALO + s * HALO_STRIDE + cg * (HH * HW * 16);
+      for (int px = lane; px < HH * HW; px += 32) {
+        const int hh = px / HW, ww = px - hh * HW;
+        const int y = th_i * TH - 1 + hh, x = tw_i * TW - 1 + ww;  // image position of this halo pixel
+        __align__(16) __half2 hv[4];
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+          float in[9];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q3 = 0; q3 < 3; ++q3) in[r * 3 + q3] = g[(hh + r) * GRAY_W + ww + q3];
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            float a0 = br[c], a1 = br[c + 1];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) { a0 = fmaf(wr[c][t], in[t], a0); a1 = fmaf(wr[c + 1][t], in[t], a1); }
+            hv[c >> 1] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hv[c] = __floats2half2_rn(0.f, 0.f);
+        }
+        *reinterpret_cast<uint4*>(halo + px * 16) = *reinterpret_cast<const uint4*>(hv);
+      }
+      fence_proxy_async_smem();             // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(&full[s]);
     }
   } else {
     // 8 epilogue warps: warp w owns TMEM lane quarter (w & 3) and the 32-column half ((w - 2) >> 2)
@@ -190,7 +259,8 @@ __global__ void __launch_bounds__(320, 1) conv3x3_halo64_kernel(const __grid_con
 static int g_num_sms = 148;
 
 int conv_halo_init() {
-  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0;
   DV_CUDA_OK(cudaGetDevice(&dev));
   DV_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -221,8 +291,12 @@ int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st) {
   p.H = pl.H; p.W = pl.W; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.total_tiles = n_img * pl.tiles_w * pl.tiles_h;
   p.bias = pl.bias; p.out = pl.out; p.out_blocked = pl.out_blocked; p.relu = pl.relu; p.pool = pl.pool;
+  p.gray = pl.gray; p.w1a = pl.w1a; p.b1a = pl.b1a;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  conv3x3_halo64_kernel<<<grid, 320, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
+  if (pl.gray)
+    conv3x3_halo64_kernel<true><<<grid, 320 + 32 * NPROD, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
+  else
+    conv3x3_halo64_kernel<false><<<grid, 320, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
   DV_CUDA_OK(cudaGetLastError());
   return DV_OK;
 }

@@ -78,6 +78,10 @@ struct HaloPlan {
   __half* out = nullptr;
   int out_blocked = 1;     // 1: [N][8][Ho][Wo][8]; 0: NHWC [N][Ho][Wo][64]
   int relu = 1, pool = 0;
+  // optional fusion of SuperPoint's conv1a (1->64) into the producer: the input is then the gray frame itself
+  const float* gray = nullptr;   // [N,H,W] fp32
+  const float* w1a = nullptr;    // [64,9]
+  const float* b1a = nullptr;    // [64]
 };
 int plan_conv3x3_halo64(HaloPlan* pl, const __half* x_blocked, int n_cap, int H, int W, const __half* w /*[64,576]*/,
                         const float* bias, __half* out, int out_blocked, int relu, int pool);

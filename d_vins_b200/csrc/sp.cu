@@ -25,6 +25,8 @@ struct SpNet {
   GemmPlan p1b, p2a, p2b, p3a, p3b, p4a, p4b, pPD, pPb, pDb;
   HaloPlan h1b, h2a, h2b;                               // weights-stationary halo kernels for the 64->64 layers
   bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
+  bool fuse1a = false;                                  // DV_SP_FUSE1A=1: conv1a inside conv1b's producer (correct, but the
+                                                        // CUDA-core producer is 3x slower than the tensor main loop - r01)
   // post
   float *smap = nullptr, *nms = nullptr;                // [B,H8,W8]
   unsigned long long* cand = nullptr;                   // [B, H8*W8]
@@ -544,6 +546,11 @@ int sp_init(Engine* e) {
   }
   // halo path: conv1a -> (blocked) -> conv1b+pool -> (blocked) -> conv2a -> (blocked) -> conv2b+pool -> NHWC
   DV_TRY(plan_conv3x3_halo64(&s->h1b, s->a1a, B, H, W, s->w[0], s->bias[0], s->a1b, 1, 1, 1));
+  {
+    const char* env = getenv("DV_SP_FUSE1A");
+    s->fuse1a = (env && env[0] == '1');
+    if (s->fuse1a) { s->h1b.gray = s->gray; s->h1b.w1a = s->w1a; s->h1b.b1a = s->b1a; }   // conv1a inside conv1b's producer
+  }
   DV_TRY(plan_conv3x3_halo64(&s->h2a, s->a1b, B, H2, W2, s->w[1], s->bias[1], s->a2a, 1, 1, 0));
   DV_TRY(plan_conv3x3_halo64(&s->h2b, s->a2a, B, H2, W2, s->w[2], s->bias[2], s->a2b, 0, 1, 1));
   DV_TRY(plan_conv3x3(&s->p1b, s->a1a, B, H, W, 64, s->w[0], 64, ep16(s->a1b, 64, s->bias[0], 1, 1)));
@@ -593,8 +600,10 @@ int sp_run_encoder(Engine* e, int b) {
   const int64_t npix = (int64_t)b * H * W;
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
   if (s->use_halo) {
-    k_conv1a_blocked<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
-    DV_CUDA_OK(cudaGetLastError());
+    if (!s->fuse1a) {
+      k_conv1a_blocked<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
+      DV_CUDA_OK(cudaGetLastError());
+    }
     {
       ProbeScope pr(e);
       DV_TRY(launch_conv_halo64(s->h1b, b, e->st));
