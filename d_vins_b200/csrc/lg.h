@@ -16,6 +16,7 @@ struct LgSeg {
 };
 
 int lg_run(Engine* e, int P, const LgSeg* segs);   // segs [2P]: (query, old) per pair; results stay on device
+int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out);
 int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float* mk0, float* mk1, int32_t* k_out);
 
 }  // namespace dv

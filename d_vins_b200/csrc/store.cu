@@ -233,11 +233,7 @@ dv_status dv_batch_match(dv_engine* h, int32_t b, const int64_t* query_ids, cons
   }
   if (which.empty()) return DV_OK;
   DV_TRY(lg_run(e, (int)which.size(), segs.data()));
-  for (size_t p = 0; p < which.size(); ++p) {
-    const int i = which[p];
-    DV_TRY(lg_fetch(e, (int)p, V, matches + (size_t)i * V * 2, mscores + (size_t)i * V, nullptr, nullptr, &k_out[i]));
-  }
-  return DV_OK;
+  return (dv_status)lg_fetch_batch(e, (int)which.size(), V, which.data(), matches, mscores, k_out);
 }
 
 }  // extern "C"
