@@ -57,6 +57,10 @@ struct LgNet {
   float* kpts = nullptr;               // [T,2] pixel keypoints (for mkpts)
   // per-call tables
   AttnJob *jobs_self = nullptr, *jobs_cross = nullptr, *h_jobs = nullptr;   // device x2, pinned host [4P]
+  AttnJobU *ju_self = nullptr, *ju_cross = nullptr, *h_ju = nullptr;        // tcgen05 attention job tables
+  CUtensorMap tm_qkv;
+  bool attn_umma = false;              // DV_LG_ATTN=umma: tcgen05 attention (lg_attn.cu; parity-green, incl. the
+                                       // MN-major V operand, but 1.8x slower than the mma.sync flash kernel so far)
   LgSeg *d_segs = nullptr, *h_segs = nullptr;                               // [2P]
   // staging for the host-vector API
   float *st_k = nullptr, *st_d = nullptr, *h_st_k = nullptr, *h_st_d = nullptr;   // [2*segcap,2], [2*segcap,256]
@@ -559,6 +563,12 @@ int lg_init(Engine* e) {
   DV_TRY(e->alloc(&g->jobs_self, (size_t)2 * P));
   DV_TRY(e->alloc(&g->jobs_cross, (size_t)2 * P));
   DV_TRY(e->alloc_pinned(&g->h_jobs, (size_t)4 * P));
+  DV_TRY(e->alloc(&g->ju_self, (size_t)2 * P));
+  DV_TRY(e->alloc(&g->ju_cross, (size_t)2 * P));
+  DV_TRY(e->alloc_pinned(&g->h_ju, (size_t)4 * P));
+  { const char* env = getenv("DV_LG_ATTN"); g->attn_umma = (env && env[0] == 'u'); }
+  DV_TRY(lg_attn_init());
+  DV_TRY(plan_lg_attn(&g->tm_qkv, g->qkv, T));
   DV_TRY(e->alloc(&g->d_segs, (size_t)2 * P + (size_t)P));     // LgSeg[2P] followed by PairDesc[P] (same size class)
   DV_TRY(e->alloc_pinned(&g->h_segs, (size_t)2 * P + (size_t)P));
   DV_TRY(e->alloc(&g->st_k, (size_t)2 * SC * 2));
@@ -702,16 +712,21 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
       const LgSeg& s = hs[2 * p + k];
       __half* base = g->qkv + (int64_t)s.off * 768;
       hj[2 * p + k] = {base, base + 256, base + 512, g->ctx + (int64_t)s.off * 256, s.n, s.n, 768, 768, 768, 256};
+      g->h_ju[2 * p + k] = {s.off, s.n, s.off, s.n, 0, 256, 512, 0};
     }
     __half* b0 = g->qkv + (int64_t)s0.off * 768;
     __half* b1 = g->qkv + (int64_t)s1.off * 768;
     hj[2 * g->P + 2 * p] = {b0, b1, b1 + 256, g->ctx + (int64_t)s0.off * 256, s0.n, s1.n, 768, 768, 768, 256};
     hj[2 * g->P + 2 * p + 1] = {b1, b0, b0 + 256, g->ctx + (int64_t)s1.off * 256, s1.n, s0.n, 768, 768, 768, 256};
+    g->h_ju[2 * g->P + 2 * p] = {s0.off, s0.n, s1.off, s1.n, 0, 0, 256, 0};          // cross: qk of the other image, its v
+    g->h_ju[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
   }
   PairDesc* d_pd = reinterpret_cast<PairDesc*>(g->d_segs + 2 * g->P);
   DV_CUDA_OK(cudaMemcpyAsync(g->d_segs, hs, sizeof(LgSeg) * 3 * g->P, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(g->jobs_self, hj, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(g->jobs_cross, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(g->ju_self, g->h_ju, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(g->ju_cross, g->h_ju + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
   k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->kpts);
   DV_LAUNCHED(e, 1);
   const dim3 agrid(cdiv(max_n_any, 64), LG_HEADS, 2 * P);
@@ -721,7 +736,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     DV_TRY(launch_gemm(L.p_qkv, T, e->st));
     if (!gemm_is_persistent())
       k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
-    k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_self, 0.125f);
+    if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_self, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+    else k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_self, 0.125f);
     DV_TRY(launch_gemm(L.p_out, T, e->st));
     if (g->fused_ffn) {
       DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
@@ -732,7 +748,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     }
     // cross block
     DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
-    k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_cross, 0.125f);
+    if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_cross, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+    else k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_cross, 0.125f);
     DV_TRY(launch_gemm(L.pc_out, T, e->st));
     if (g->fused_ffn) {
       DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));

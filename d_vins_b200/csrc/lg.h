@@ -15,8 +15,21 @@ struct LgSeg {
   int off;      // first row in the packed token buffers (filled by lg_run)
 };
 
+// tcgen05 attention (lg_attn.cu): operands are windows of the packed qkv buffer [T,768]
+struct AttnJobU { int q_row, nq, k_row, nk, q_col, k_col, v_col, pad; };
+
 int lg_run(Engine* e, int P, const LgSeg* segs);   // segs [2P]: (query, old) per pair; results stay on device
 int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out);
 int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float* mk0, float* mk1, int32_t* k_out);
 
+}  // namespace dv
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+namespace dv {
+int lg_attn_init();
+int plan_lg_attn(CUtensorMap* tm, const __half* qkv, int T_cap);
+int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, float scale,
+                   cudaStream_t st);
 }  // namespace dv

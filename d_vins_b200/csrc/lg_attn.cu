@@ -1,0 +1,215 @@
+// LightGlue attention on tcgen05 (self- and cross-attention share it): one CTA per (job, head, 128-query tile).
+//
+//   S[128 x 128] = Q K^T        Q, K tiles: 64-wide (head_dim) K-major SWIZZLE_128B rows brought by TMA straight from the
+//                               packed qkv buffer [T,768]; accumulator in TMEM columns [0,128)
+//   softmax (online)            4 warps, thread == query row: two passes of tcgen05.ld over the S row (max, then exp2 /
+//                               sum); P is written as fp16 into shared memory in the K-major SWIZZLE_128B layout of an
+//                               A operand (two 128x64 tiles)
+//   O_chunk[128 x 64] = P V     V tile rows are keys (the MMA's K) with head_dim contiguous: an MN-major B operand, i.e.
+//                               the tile exactly as TMA delivers it - no transpose; accumulator in TMEM columns [128,192)
+//   O = O * corr + O_chunk      in registers of the row-owning thread (no TMEM read-modify-write)
+//
+// Replaces the mma.sync flash kernel of lg.cu (kept behind DV_LG_ATTN=mma): r01 launch lists had it at 77 us per launch
+// (~130 TFLOP/s, legacy HMMA pipe) = 34 % of the LightGlue stage.  Here the tensor work is 12 tcgen05.mma per 128-key
+// chunk and the bound becomes the 128x128 exp2 per chunk on the MUFU pipe.
+#include "common.cuh"
+#include "gemm.h"
+#include "lg.h"
+#include "umma.cuh"
+#include "../../include/dvins_perception.h"
+
+namespace dv {
+
+namespace {
+constexpr int TILE_BYTES = 128 * 128;          // 128 rows x 64 halves
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = TILE_BYTES;              // 2 stages
+constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
+constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;  // two 128x64 tiles
+constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+}  // namespace
+
+__global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                              const AttnJobU* __restrict__ jobs,
+                                                              __half* __restrict__ ctx, float sl2) {
+  const AttnJobU jb = jobs[blockIdx.z];
+  const int q0 = blockIdx.x * 128;
+  if (q0 >= jb.nq) return;                     // uniform per CTA
+  const int head = blockIdx.y;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* kv_full = q_full + 1;              // [2]
+  uint64_t* kv_empty = kv_full + 2;            // [2]
+  uint64_t* s_full = kv_empty + 2;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* o_full = p_ready + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = (jb.nk + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(smem + OFF_Q, &tmQKV, q_full, jb.q_col + head * 64, jb.q_row + q0);
+      for (int j = 0; j < n_chunks; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+        tma_load_2d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &kv_full[s], jb.k_col + head * 64, jb.k_row + j * 128);
+        tma_load_2d(smem + OFF_V + s * TILE_BYTES, &tmQKV, &kv_full[s], jb.v_col + head * 64, jb.k_row + j * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_s = make_idesc_f16_f32(128, 128);                 // A, B K-major
+      constexpr uint32_t idesc_pv = make_idesc_f16_f32(128, 64) | (1u << 16);    // B (= V) MN-major
+      const uint64_t dq = make_desc_sw128(smem_u32(smem + OFF_Q));
+      const uint64_t dp = make_desc_sw128(smem_u32(smem + OFF_P));
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_chunks; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_desc_sw128(smem_u32(smem + OFF_K + s * TILE_BYTES));
+        const uint64_t dv = make_desc_sw128(smem_u32(smem + OFF_V + s * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)                                             // head_dim 64 = 4 k-steps
+          tc_mma_f16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+        tc_commit(s_full);
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)                                             // 128 keys = 8 k-steps of 16
+          // A: P tile (k >> 2), 32-byte step inside its 128-byte rows.  B: V rows [16k, 16k+16) = +2048 bytes.
+          tc_mma_f16(tmem_base + 128, dp + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
+                     dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)(k != 0));
+        tc_commit(o_full);
+        tc_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction: thread == query row
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = smem + OFF_P + row * 128;
+    for (int j = 0; j < n_chunks; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * 128;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tl + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m_run, mx);                 // finite: every chunk holds >= 1 valid key
+      const float corr = exp2f((m_run - m_new) * sl2);
+      const float mb = m_new * sl2;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tl + c * 32, r);
+        tmem_ld_wait();
+        __align__(16) __half2 hv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int key = kbase + c * 32 + 2 * i;
+          const float p0 = key < jb.nk ? exp2f(fmaf(__uint_as_float(r[2 * i]), sl2, -mb)) : 0.f;
+          const float p1 = key + 1 < jb.nk ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb)) : 0.f;
+          hv[i] = __floats2half2_rn(p0, p1);
+          // the row sum uses the fp16-rounded probabilities that the PV product actually sees
+          const float2 pr = __half22float2(hv[i]);
+          sum += pr.x + pr.y;
+        }
+        uint8_t* tile = prow + (c >> 1) * TILE_BYTES;
+        const int ch0 = (c & 1) * 4;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<uint4*>(tile + (((ch0 + g) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[g];
+      }
+      l_run = l_run * corr + sum;
+      m_run = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(p_ready);
+#pragma unroll
+      for (int i = 0; i < 64; ++i) o[i] *= corr;
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tl + 128 + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
+      }
+      tc_fence_before();     // order these TMEM reads before the next chunk's MMAs (released through p_ready / s_full)
+    }
+    if (q0 + row < jb.nq) {
+      const float inv = 1.f / l_run;
+      __half* op = ctx + (int64_t)(jb.q_row + q0 + row) * 256 + head * 64;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        __align__(16) __half2 hv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(o[g * 8 + 2 * i] * inv, o[g * 8 + 2 * i + 1] * inv);
+        reinterpret_cast<uint4*>(op)[g] = *reinterpret_cast<const uint4*>(hv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int lg_attn_init() {
+  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  return DV_OK;
+}
+
+int plan_lg_attn(CUtensorMap* tm, const __half* qkv, int T_cap) {
+  const uint64_t dims[2] = {768, (uint64_t)T_cap}, strides[1] = {1536};
+  const uint32_t box[2] = {64, 128};
+  return tmap_encode_f16(tm, qkv, 2, dims, strides, box, true);
+}
+
+int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, float scale,
+                   cudaStream_t st) {
+  if (n_jobs <= 0) return DV_OK;
+  const dim3 grid(cdiv(max_nq, 128), 4, n_jobs);
+  lg_attn_umma_kernel<<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f);
+  DV_CUDA_OK(cudaGetLastError());
+  return DV_OK;
+}
+
+}  // namespace dv
