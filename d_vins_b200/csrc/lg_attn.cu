@@ -12,6 +12,9 @@
 // Replaces the mma.sync flash kernel of lg.cu (kept behind DV_LG_ATTN=mma): r01 launch lists had it at 77 us per launch
 // (~130 TFLOP/s, legacy HMMA pipe) = 34 % of the LightGlue stage.  Here the tensor work is 12 tcgen05.mma per 128-key
 // chunk and the bound becomes the 128x128 exp2 per chunk on the MUFU pipe.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.h"
 #include "lg.h"
@@ -30,9 +33,15 @@ constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
 }  // namespace
 
+__device__ __forceinline__ float ex2_approx(float x) {     // one MUFU op (exp2f adds range fix-ups around it)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                               const AttnJobU* __restrict__ jobs,
-                                                              __half* __restrict__ ctx, float sl2) {
+                                                              __half* __restrict__ ctx, float sl2, long long* dbg) {
   const AttnJobU jb = jobs[blockIdx.z];
   const int q0 = blockIdx.x * 128;
   if (q0 >= jb.nq) return;                     // uniform per CTA
@@ -93,8 +102,8 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
         tc_commit(s_full);
         mbar_wait(p_ready, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)                                             // 128 keys = 8 k-steps of 16
+        const int pv_steps = min(8, (jb.nk - j * 128 + 15) >> 4);                // only the k-steps that hold valid keys
+        for (int k = 0; k < pv_steps; ++k)                                      // up to 128 keys = 8 k-steps of 16
           // A: P tile (k >> 2), 32-byte step inside its 128-byte rows.  B: V rows [16k, 16k+16) = +2048 bytes.
           tc_mma_f16(tmem_base + 128, dp + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
                      dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)(k != 0));
@@ -112,39 +121,65 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
     for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = smem + OFF_P + row * 128;
+    const bool warp_live = q0 + q * 32 < jb.nq;
+    const bool dbgt = dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 1 && threadIdx.x == 64;
     for (int j = 0; j < n_chunks; ++j) {
+      const long long t0 = dbgt ? clock64() : 0;
       mbar_wait(s_full, j & 1);
+      const long long t1 = dbgt ? clock64() : 0;
       tc_fence_after();
       const int kbase = j * 128;
+      const int ngrp = min(4, (jb.nk - kbase + 31) >> 5);    // 32-key groups holding valid keys (PV reads no further)
+      if (!warp_live) {                                      // every row of this warp is >= nq: nothing to compute
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cnt(p_ready);
+        mbar_wait(o_full, j & 1);
+        continue;
+      }
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < ngrp; ++c) {
         uint32_t r[32];
         tmem_ld32(tl + c * 32, r);
         tmem_ld_wait();
+        if (kbase + c * 32 + 32 <= jb.nk) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
+      const long long t2 = dbgt ? clock64() : 0;
       const float m_new = fmaxf(m_run, mx);                 // finite: every chunk holds >= 1 valid key
       const float corr = exp2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
       float sum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < ngrp; ++c) {
         uint32_t r[32];
         tmem_ld32(tl + c * 32, r);
         tmem_ld_wait();
         __align__(16) __half2 hv[16];
+        if (kbase + c * 32 + 32 <= jb.nk) {                 // full 32-key group (warp-uniform): no masking
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int key = kbase + c * 32 + 2 * i;
-          const float p0 = key < jb.nk ? exp2f(fmaf(__uint_as_float(r[2 * i]), sl2, -mb)) : 0.f;
-          const float p1 = key + 1 < jb.nk ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb)) : 0.f;
-          hv[i] = __floats2half2_rn(p0, p1);
-          // the row sum uses the fp16-rounded probabilities that the PV product actually sees
-          const float2 pr = __half22float2(hv[i]);
-          sum += pr.x + pr.y;
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb));
+            hv[i] = __floats2half2_rn(p0, p1);
+            sum += p0 + p1;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int key = kbase + c * 32 + 2 * i;
+            const float p0 = key < jb.nk ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mb)) : 0.f;
+            const float p1 = key + 1 < jb.nk ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb)) : 0.f;
+            hv[i] = __floats2half2_rn(p0, p1);
+            sum += p0 + p1;
+          }
         }
         uint8_t* tile = prow + (c >> 1) * TILE_BYTES;
         const int ch0 = (c & 1) * 4;
@@ -158,9 +193,11 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(p_ready);
+      const long long t3 = dbgt ? clock64() : 0;
 #pragma unroll
       for (int i = 0; i < 64; ++i) o[i] *= corr;
       mbar_wait(o_full, j & 1);
+      const long long t4 = dbgt ? clock64() : 0;
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -171,6 +208,10 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
         for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
       }
       tc_fence_before();     // order these TMEM reads before the next chunk's MMAs (released through p_ready / s_full)
+      if (dbgt) {
+        const long long t5 = clock64();
+        dbg[0] += t1 - t0; dbg[1] += t2 - t1; dbg[2] += t3 - t2; dbg[3] += t4 - t3; dbg[4] += t5 - t4; dbg[5] += 1;
+      }
     }
     if (q0 + row < jb.nq) {
       const float inv = 1.f / l_run;
@@ -207,8 +248,19 @@ int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int 
                    cudaStream_t st) {
   if (n_jobs <= 0) return DV_OK;
   const dim3 grid(cdiv(max_nq, 128), 4, n_jobs);
-  lg_attn_umma_kernel<<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f);
+  static long long* d_dbg = nullptr;
+  static const bool want = getenv("DV_ATTN_DBG") != nullptr;       // diagnostics: softmax-thread cycle counters
+  static int calls = 0;
+  if (want && !d_dbg) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+  lg_attn_umma_kernel<<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
   DV_CUDA_OK(cudaGetLastError());
+  if (want && ++calls == 18) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[attn dbg] chunks %lld | cycles/chunk: wait S %lld, pass A (max) %lld, pass B (exp+P) %lld, wait O %lld, O acc %lld\n",
+            h[5], h[0] / h[5], h[1] / h[5], h[2] / h[5], h[3] / h[5], h[4] / h[5]);
+  }
   return DV_OK;
 }
 
