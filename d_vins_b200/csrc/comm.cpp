@@ -55,6 +55,13 @@ int comm_allgather(Engine* e, const float* send, float* recv, size_t count_per_r
   return DV_OK;
 }
 
+int comm_allgather_bytes(Engine* e, const void* send, void* recv, size_t bytes_per_rank) {
+  if (!e->comm || !e->comm->comm) { set_error("world_size > 1 but dv_comm_init was not called"); return DV_ERR_COMM; }
+  ncclResult_t r = g_api->AllGather(send, recv, bytes_per_rank, ncclInt8, e->comm->comm, e->st);
+  if (r != ncclSuccess) return nccl_fail("ncclAllGather", r);
+  return DV_OK;
+}
+
 void comm_free(Engine* e) {
   if (e->comm) {
     if (e->comm->comm && g_api) g_api->CommDestroy(e->comm->comm);
@@ -92,7 +99,7 @@ dv_status dv_comm_init(dv_engine* h, const void* id128) {
   memcpy(&id, id128, 128);
   ncclResult_t r = g_api->CommInitRank(&e->comm->comm, e->cfg.world_size, id, e->cfg.rank);
   if (r != ncclSuccess) { comm_free(e); return (dv_status)nccl_fail("ncclCommInitRank", r); }
-  return DV_OK;
+  return (dv_status)store_exchange_peers(e);     // CUDA-IPC views of every rank's feature store (one-sided P2P pulls)
 }
 
 }  // extern "C"

@@ -138,5 +138,6 @@ void bank_free(Engine* e);
 int store_init(Engine* e);                    // store.cu
 void store_free(Engine* e);
 void comm_free(Engine* e);                    // comm.cpp
+int store_exchange_peers(Engine* e);          // store.cu (called by dv_comm_init)
 
 }  // namespace dv

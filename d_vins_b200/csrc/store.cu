@@ -11,6 +11,7 @@
 namespace dv {
 
 int comm_allgather(Engine* e, const float* send, float* recv, size_t count_per_rank);   // comm.cpp
+int comm_allgather_bytes(Engine* e, const void* send, void* recv, size_t bytes_per_rank);
 float* bank_rows(Engine* e);
 float* bank_query_buf(Engine* e);
 int64_t& bank_size_ref(Engine* e);
@@ -26,7 +27,33 @@ struct Store {
   float* h_vio = nullptr; int* h_nvio = nullptr; int* h_nsp = nullptr; int* d_slot = nullptr; int* h_slot = nullptr;
   std::vector<int64_t> cur_ids;
   int cur_b = 0;
+  // ---- multi-GPU: every rank's store is mapped here through CUDA IPC, and each round's all-gather also carries the
+  // (frame id, n_sp, n_vio) of the new keyframes, so LightGlue can PULL an old keyframe's features from its owner rank
+  // with a one-sided peer copy over NVLink (SURVEY §8(e) "LightGlue operand locality", option (ii)).
+  std::vector<float*> peer_kpts, peer_desc;                 // [world]; own rank = local pointers
+  std::vector<std::vector<int64_t>> r_frame_id;             // [world][slots]
+  std::vector<std::vector<int>> r_n_sp, r_n_vio;            // [world][slots]
+  float *send516 = nullptr, *recv516 = nullptr;             // [b,516] / [world*b,516] round buffers
+  int *d_meta = nullptr, *h_meta = nullptr;                 // this rank's [b,4] meta (device / pinned)
+  int *d_meta_all = nullptr, *h_meta_all = nullptr;         // gathered [world*b,4]
+  float *cache_kpts = nullptr, *cache_desc = nullptr;       // [B, cap, *] landing zone of pulled keyframes
+  bool peers_open = false;
 };
+
+// send row i = [ gdesc_i (512 f32) | frame id lo, hi, n_sp, n_vio (bit patterns) ]
+__global__ void k_round_pack(const float* __restrict__ gdesc, const int* __restrict__ meta, float* __restrict__ send) {
+  const int i = blockIdx.x;
+  for (int c = threadIdx.x; c < 516; c += blockDim.x)
+    send[(int64_t)i * 516 + c] = c < 512 ? gdesc[(int64_t)i * 512 + c] : __int_as_float(meta[i * 4 + c - 512]);
+}
+__global__ void k_round_unpack(const float* __restrict__ recv, float* __restrict__ bank_dst, int* __restrict__ meta_all) {
+  const int i = blockIdx.x;
+  for (int c = threadIdx.x; c < 516; c += blockDim.x) {
+    const float v = recv[(int64_t)i * 516 + c];
+    if (c < 512) bank_dst[(int64_t)i * 512 + c] = v;
+    else meta_all[i * 4 + c - 512] = __float_as_int(v);
+  }
+}
 
 // one block per (frame, row chunk): rows [0,n_sp) from the SuperPoint outputs, rows [n_sp, n_sp+n_vio) from SP_RE
 __global__ void k_store_write(const float* __restrict__ sp_kpts, const float* __restrict__ sp_desc,
@@ -66,9 +93,70 @@ int store_init(Engine* e) {
   DV_TRY(e->alloc_pinned(&s->h_nsp, (size_t)e->B));
   DV_TRY(e->alloc_pinned(&s->h_slot, (size_t)e->B));
   DV_TRY(e->alloc(&s->d_slot, (size_t)e->B));
+  const int ws = e->cfg.world_size;
+  s->peer_kpts.assign(ws, nullptr); s->peer_desc.assign(ws, nullptr);
+  s->peer_kpts[e->cfg.rank] = s->kpts; s->peer_desc[e->cfg.rank] = s->desc;
+  s->r_frame_id.assign(ws, std::vector<int64_t>(s->slots, -1));
+  s->r_n_sp.assign(ws, std::vector<int>(s->slots, 0));
+  s->r_n_vio.assign(ws, std::vector<int>(s->slots, 0));
+  if (ws > 1) {
+    DV_TRY(e->alloc(&s->send516, (size_t)e->B * 516));
+    DV_TRY(e->alloc(&s->recv516, (size_t)ws * e->B * 516));
+    DV_TRY(e->alloc(&s->d_meta, (size_t)e->B * 4));
+    DV_TRY(e->alloc_pinned(&s->h_meta, (size_t)e->B * 4));
+    DV_TRY(e->alloc(&s->d_meta_all, (size_t)ws * e->B * 4));
+    DV_TRY(e->alloc_pinned(&s->h_meta_all, (size_t)ws * e->B * 4));
+    DV_TRY(e->alloc(&s->cache_kpts, (size_t)e->B * s->cap * 2));
+    DV_TRY(e->alloc(&s->cache_desc, (size_t)e->B * s->cap * 256));
+  }
   return DV_OK;
 }
-void store_free(Engine* e) { delete e->store; e->store = nullptr; }
+void store_free(Engine* e) {
+  Store* s = e->store;
+  if (s && s->peers_open)
+    for (int r = 0; r < e->cfg.world_size; ++r)
+      if (r != e->cfg.rank) {
+        if (s->peer_kpts[r]) cudaIpcCloseMemHandle(s->peer_kpts[r]);
+        if (s->peer_desc[r]) cudaIpcCloseMemHandle(s->peer_desc[r]);
+      }
+  delete e->store;
+  e->store = nullptr;
+}
+
+// Exchange CUDA-IPC handles of the store buffers through the (already initialised) NCCL communicator and map every
+// peer's store into this process.
+int store_exchange_peers(Engine* e) {
+  Store* s = e->store;
+  const int ws = e->cfg.world_size, me = e->cfg.rank;
+  if (ws <= 1 || s->peers_open) return DV_OK;
+  struct Handles { cudaIpcMemHandle_t k, d; };
+  Handles mine;
+  DV_CUDA_OK(cudaIpcGetMemHandle(&mine.k, s->kpts));
+  DV_CUDA_OK(cudaIpcGetMemHandle(&mine.d, s->desc));
+  Handles *d_send = nullptr, *d_recv = nullptr;
+  DV_CUDA_OK(cudaMalloc(&d_send, sizeof(Handles)));
+  DV_CUDA_OK(cudaMalloc(&d_recv, sizeof(Handles) * ws));
+  DV_CUDA_OK(cudaMemcpyAsync(d_send, &mine, sizeof(Handles), cudaMemcpyHostToDevice, e->st));
+  int rc = comm_allgather_bytes(e, d_send, d_recv, sizeof(Handles));
+  std::vector<Handles> all(ws);
+  if (!rc) {
+    cudaError_t ce = cudaMemcpyAsync(all.data(), d_recv, sizeof(Handles) * ws, cudaMemcpyDeviceToHost, e->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    if (ce != cudaSuccess) { set_error(std::string("store_exchange_peers: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
+  }
+  cudaFree(d_send); cudaFree(d_recv);
+  if (rc) return rc;
+  for (int r = 0; r < ws; ++r) {
+    if (r == me) continue;
+    void *pk = nullptr, *pd = nullptr;
+    DV_CUDA_OK(cudaIpcOpenMemHandle(&pk, all[r].k, cudaIpcMemLazyEnablePeerAccess));
+    DV_CUDA_OK(cudaIpcOpenMemHandle(&pd, all[r].d, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_kpts[r] = reinterpret_cast<float*>(pk);
+    s->peer_desc[r] = reinterpret_cast<float*>(pd);
+  }
+  s->peers_open = true;
+  return DV_OK;
+}
 
 }  // namespace dv
 
@@ -163,9 +251,30 @@ dv_status dv_batch_commit(dv_engine* h, int32_t b, int64_t* first_row) {
   if (ws == 1) {
     DV_CUDA_OK(cudaMemcpyAsync(dst, g, sizeof(float) * 512 * b, cudaMemcpyDeviceToDevice, e->st));
   } else {
-    // the single collective of the path: rank-major landing == global frame order when frame t -> rank t % P
-    DV_TRY(comm_allgather(e, g, dst, (size_t)512 * b));
-    DV_LAUNCHED(e, 1);
+    // the single collective of the path: [b, 512 + 4] rows per rank (global descriptor + keyframe id / point counts),
+    // gathered rank-major == global frame order; unpacked straight into the bank tail.
+    Store* s = e->store;
+    for (int i = 0; i < b; ++i) {
+      const int64_t fid = s->cur_ids[i];
+      const int sl = (int)(fid % s->slots);
+      s->h_meta[i * 4 + 0] = (int)(fid & 0xffffffffll); s->h_meta[i * 4 + 1] = (int)(fid >> 32);
+      s->h_meta[i * 4 + 2] = s->n_sp[sl]; s->h_meta[i * 4 + 3] = s->n_vio[sl];
+    }
+    DV_CUDA_OK(cudaMemcpyAsync(s->d_meta, s->h_meta, sizeof(int) * 4 * b, cudaMemcpyHostToDevice, e->st));
+    k_round_pack<<<b, 128, 0, e->st>>>(g, s->d_meta, s->send516);
+    DV_TRY(comm_allgather(e, s->send516, s->recv516, (size_t)516 * b));
+    k_round_unpack<<<ws * b, 128, 0, e->st>>>(s->recv516, dst, s->d_meta_all);
+    DV_CUDA_OK(cudaGetLastError());
+    DV_LAUNCHED(e, 3);
+    DV_CUDA_OK(cudaMemcpyAsync(s->h_meta_all, s->d_meta_all, sizeof(int) * 4 * ws * b, cudaMemcpyDeviceToHost, e->st));
+    DV_CUDA_OK(cudaStreamSynchronize(e->st));
+    for (int r = 0; r < ws; ++r)
+      for (int i = 0; i < b; ++i) {
+        const int* m = s->h_meta_all + ((size_t)r * b + i) * 4;
+        const int64_t fid = ((int64_t)m[1] << 32) | (uint32_t)m[0];
+        const int sl = (int)(fid % s->slots);
+        s->r_frame_id[r][sl] = fid; s->r_n_sp[r][sl] = m[2]; s->r_n_vio[r][sl] = m[3];
+      }
   }
   if (first_row) *first_row = size + (int64_t)e->cfg.rank * b;
   size += (int64_t)ws * b;
@@ -216,19 +325,34 @@ dv_status dv_batch_match(dv_engine* h, int32_t b, const int64_t* query_ids, cons
   std::vector<int> which;
   for (int i = 0; i < b; ++i) {
     k_out[i] = 0;
+    if (query_ids[i] < 0 || old_ids[i] < 0) { set_error("dv_batch_match: negative keyframe id"); return DV_ERR_INVALID; }
     const int qs = (int)(query_ids[i] % s->slots), os = (int)(old_ids[i] % s->slots);
-    if (query_ids[i] < 0 || old_ids[i] < 0 || s->frame_id[qs] != query_ids[i] || s->frame_id[os] != old_ids[i]) {
-      set_error("dv_batch_match: keyframe not resident in this rank's store");
-      return DV_ERR_INVALID;
-    }
-    const int m = s->n_vio[qs], n = s->n_sp[os] + s->n_vio[os];
+    if (s->frame_id[qs] != query_ids[i]) { set_error("dv_batch_match: query keyframe not resident in this rank's store"); return DV_ERR_INVALID; }
+    // the old keyframe: local store, else the owner rank's store (one-sided pull over NVLink)
+    int owner = -1, n_sp_old = 0, n_vio_old = 0;
+    if (s->frame_id[os] == old_ids[i]) { owner = e->cfg.rank; n_sp_old = s->n_sp[os]; n_vio_old = s->n_vio[os]; }
+    else if (s->peers_open)
+      for (int r = 0; r < e->cfg.world_size && owner < 0; ++r)
+        if (r != e->cfg.rank && s->r_frame_id[r][os] == old_ids[i]) { owner = r; n_sp_old = s->r_n_sp[r][os]; n_vio_old = s->r_n_vio[r][os]; }
+    if (owner < 0) { set_error("dv_batch_match: old keyframe not resident on any rank's store"); return DV_ERR_INVALID; }
+    const int m = s->n_vio[qs], n = n_sp_old + n_vio_old;
     // keyframe.cpp:373,:935 - the reference skips SP_RE / LightGlue for <= 20 window points; engine floor is 10
     if (m < 10 || n < 10) continue;
     if (n > e->cfg.lg_max_kpts) { set_error("dv_batch_match: old keyframe exceeds lg_max_kpts"); return DV_ERR_CAPACITY; }
     const float* qk = s->kpts + ((size_t)qs * s->cap + s->n_sp[qs]) * 2;
     const float* qd = s->desc + ((size_t)qs * s->cap + s->n_sp[qs]) * 256;
     segs.push_back({qk, qd, m, e->W, e->H, 0});
-    segs.push_back({s->kpts + (size_t)os * s->cap * 2, s->desc + (size_t)os * s->cap * 256, n, e->W, e->H, 0});
+    const float* ok = s->kpts + (size_t)os * s->cap * 2;
+    const float* od = s->desc + (size_t)os * s->cap * 256;
+    if (owner != e->cfg.rank) {
+      StageScope sc(e, ST_COPY);
+      float* ck = s->cache_kpts + (size_t)which.size() * s->cap * 2;
+      float* cd = s->cache_desc + (size_t)which.size() * s->cap * 256;
+      DV_CUDA_OK(cudaMemcpyAsync(ck, s->peer_kpts[owner] + (size_t)os * s->cap * 2, sizeof(float) * 2 * n, cudaMemcpyDeviceToDevice, e->st));
+      DV_CUDA_OK(cudaMemcpyAsync(cd, s->peer_desc[owner] + (size_t)os * s->cap * 256, sizeof(float) * 256 * n, cudaMemcpyDeviceToDevice, e->st));
+      ok = ck; od = cd;
+    }
+    segs.push_back({ok, od, n, e->W, e->H, 0});
     which.push_back(i);
   }
   if (which.empty()) return DV_OK;
