@@ -79,28 +79,35 @@ __global__ void k_mix_pre(const uint8_t* __restrict__ img, int H, int W, int ch,
 }
 
 // 7x7 stride-2 pad-3 im2col of the 3-channel image: out [B*160*160, 192], k = (r*7+s)*3 + c, zero-padded to 192.
-__global__ void k_im2col_stem(const __half* __restrict__ img, __half* __restrict__ out, int64_t total8) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
-  const int64_t m = i / 24;
-  const int k0 = (int)(i - m * 24) * 8;
-  const int b = (int)(m / 25600);
-  const int p = (int)(m - (int64_t)b * 25600);
-  const int oy = p / 160, ox = p - oy * 160;
-  __align__(16) __half v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = k0 + j;
-    __half val = __float2half(0.f);
-    if (k < 147) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int r = tap / 7, s = tap - r * 7;
-      const int iy = oy * 2 + r - 3, ix = ox * 2 + s - 3;
-      if (iy >= 0 && iy < 320 && ix >= 0 && ix < 320) val = img[(((int64_t)b * 320 + iy) * 320 + ix) * 3 + c];
-    }
-    v[j] = val;
+// One block per (frame, output row, 32 output columns): the 7 x 69 x 3 input window is staged once in shared memory
+// (each input row is one contiguous 414-byte read); a pixel's 21 values of filter row r are contiguous there, so
+// k -> smem[r*207 + ox*6 + k%21].  Stores are 16-byte, 384 contiguous bytes per output row.
+#define STEM_OXB 32
+#define STEM_ROWLEN ((2 * STEM_OXB + 5) * 3)   // 207
+__global__ void __launch_bounds__(256) k_im2col_stem(const __half* __restrict__ img, __half* __restrict__ out) {
+  __shared__ __half tile[7 * STEM_ROWLEN];
+  const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * STEM_OXB;
+  const int ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < 7 * STEM_ROWLEN; i += blockDim.x) {
+    const int r = i / STEM_ROWLEN, q = i - r * STEM_ROWLEN;
+    const int iy = oy * 2 + r - 3, ix = ix0 + q / 3;
+    __half v = __float2half(0.f);
+    if (iy >= 0 && iy < 320 && ix >= 0 && ix < 320) v = img[(((int64_t)b * 320 + iy) * 320 + ix0) * 3 + q];
+    tile[i] = v;
   }
-  *reinterpret_cast<uint4*>(out + i * 8) = *reinterpret_cast<uint4*>(v);
+  __syncthreads();
+  for (int q = threadIdx.x; q < STEM_OXB * 24; q += blockDim.x) {
+    const int px = q / 24, k0 = (q - px * 24) * 8;
+    __align__(16) __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      const int r = k / 21;
+      v[j] = (k < 147) ? tile[r * STEM_ROWLEN + px * 6 + (k - r * 21)] : __float2half(0.f);
+    }
+    const int64_t m = ((int64_t)b * 160 + oy) * 160 + ox0 + px;
+    *reinterpret_cast<uint4*>(out + m * 192 + k0) = *reinterpret_cast<uint4*>(v);
+  }
 }
 
 // 3x3 stride-2 pad-1 im2col over NHWC (C % 8 == 0): out [B*Ho*Wo, 9*C], k = (r*3+s)*C + c.
@@ -364,8 +371,7 @@ int mix_init(Engine* e) {
     const int total = b * 320 * 320;
     k_mix_pre<<<cdiv(total, 256), 256, 0, en->st>>>(en->d_img, en->H, en->W, en->img_ch, mm->d2i[0], mm->d2i[1],
                                                    mm->d2i[2], mm->d2i[3], mm->d2i[4], mm->d2i[5], mm->img16, total);
-    const int64_t t8 = (int64_t)b * 25600 * 24;
-    k_im2col_stem<<<(unsigned)cdiv64(t8, 256), 256, 0, en->st>>>(mm->img16, mm->col, t8);
+    k_im2col_stem<<<dim3(160 / STEM_OXB, 160, b), 256, 0, en->st>>>(mm->img16, mm->col);
     return (int)DV_OK;
   });
   m->n_launch += 2;

@@ -194,14 +194,15 @@ __global__ void k_softmax_d2s(const float* __restrict__ logits, int ld, float* _
 
 // 9-tap running max over a strip of L outputs in registers: 4 max ops per output (pairwise doubling) and ONE shared
 // memory load per input instead of 9.  Taps outside [0, n) are -inf (region edge == torch's implicit -inf padding).
-template <int L>
-__device__ __forceinline__ void strip_max9(const float* __restrict__ in, float* __restrict__ out, int stride, int p0,
-                                           int n) {
+// `ld(p)` produces input p, `st(p, m)` consumes the 9-tap max at p: the elementwise steps between NMS's max-pools
+// (mask -> 0/1, suppressed scores, equality tests) ride inside the passes instead of being separate sweeps.
+template <int L, class LD, class ST>
+__device__ __forceinline__ void strip_max9(LD ld, ST st, int p0, int n) {
   float v[L + 8];
 #pragma unroll
   for (int i = 0; i < L + 8; ++i) {
     const int p = p0 + i - 4;
-    v[i] = (p >= 0 && p < n) ? in[p * stride] : -INFINITY;
+    v[i] = (p >= 0 && p < n) ? ld(p) : -INFINITY;
   }
   float m2[L + 7];
 #pragma unroll
@@ -212,7 +213,7 @@ __device__ __forceinline__ void strip_max9(const float* __restrict__ in, float* 
 #pragma unroll
   for (int i = 0; i < L; ++i) {
     const float m8 = fmaxf(m4[i], m4[i + 4]);
-    if (p0 + i < n) out[(p0 + i) * stride] = fmaxf(m8, v[i + 8]);
+    if (p0 + i < n) st(p0 + i, fmaxf(m8, v[i + 8]));
   }
 }
 
@@ -220,13 +221,16 @@ __device__ __forceinline__ void strip_max9(const float* __restrict__ in, float* 
 #define NMS_ROW_STRIP 26     // 104 = 4 x 26
 #define NMS_COL_STRIP 24     // 72  = 3 x 24
 
-__device__ __forceinline__ void maxpool9_inplace(float* T2, float* T1) {
-  // T1 = rowmax(T2); T2 = colmax(T1)
+// 9x9 max-pool of the region: T1 = rowmax(in(i)); out(i, colmax(T1)); both functors take the linear region index.
+template <class IN, class OUT>
+__device__ __forceinline__ void maxpool9(IN in, OUT out, float* T1) {
   {
     const int t = threadIdx.x;
     if (t < NMS_RH * (NMS_RW / NMS_ROW_STRIP)) {
       const int row = t / (NMS_RW / NMS_ROW_STRIP), sp = t - row * (NMS_RW / NMS_ROW_STRIP);
-      strip_max9<NMS_ROW_STRIP>(T2 + row * NMS_RW, T1 + row * NMS_RW, 1, sp * NMS_ROW_STRIP, NMS_RW);
+      const int base = row * NMS_RW;
+      strip_max9<NMS_ROW_STRIP>([&](int p) { return in(base + p); }, [&](int p, float m) { T1[base + p] = m; },
+                                sp * NMS_ROW_STRIP, NMS_RW);
     }
   }
   __syncthreads();
@@ -234,7 +238,8 @@ __device__ __forceinline__ void maxpool9_inplace(float* T2, float* T1) {
     const int t = threadIdx.x;
     if (t < NMS_RW * (NMS_RH / NMS_COL_STRIP)) {
       const int sp = t / NMS_RW, col = t - sp * NMS_RW;
-      strip_max9<NMS_COL_STRIP>(T1 + col, T2 + col, NMS_RW, sp * NMS_COL_STRIP, NMS_RH);
+      strip_max9<NMS_COL_STRIP>([&](int p) { return T1[p * NMS_RW + col]; },
+                                [&](int p, float m) { out(p * NMS_RW + col, m); }, sp * NMS_COL_STRIP, NMS_RH);
     }
   }
   __syncthreads();
@@ -246,8 +251,7 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_select(const float* __restr
   extern __shared__ float sm[];
   float* S = sm;
   float* T1 = S + NMS_RN;
-  float* T2 = T1 + NMS_RN;
-  uint8_t* MM = reinterpret_cast<uint8_t*>(T2 + NMS_RN);
+  uint8_t* MM = reinterpret_cast<uint8_t*>(T1 + NMS_RN);
   uint8_t* SUPP = MM + NMS_RN;
   const int b = blockIdx.z;
   const int gx0 = blockIdx.x * NMS_TW - NMS_HALO, gy0 = blockIdx.y * NMS_TH - NMS_HALO;
@@ -257,40 +261,29 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_select(const float* __restr
     const int y = i / NMS_RW, x = i - y * NMS_RW;
     const int gy = gy0 + y, gx = gx0 + x;
     const bool in = gy >= 0 && gy < H8 && gx >= 0 && gx < W8;
-    const float v = in ? src[(int64_t)gy * W8 + gx] : NEG;
-    S[i] = v;
-    T2[i] = v;
+    S[i] = in ? src[(int64_t)gy * W8 + gx] : NEG;
   }
   __syncthreads();
-  maxpool9_inplace(T2, T1);
-  for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
-    const float v = S[i];
-    MM[i] = (v != NEG) && (v == T2[i]);
-  }
-  __syncthreads();
+  // export/superpoint.py:52-66 simple_nms: max_mask = scores == max_pool(scores); two rounds of
+  // supp = max_pool(mask) > 0; supp_scores = where(supp, 0, scores); mask |= (supp_scores == max_pool(supp_scores)) & ~supp
+  maxpool9([&](int i) { return S[i]; },
+           [&](int i, float m) {
+             const float v = S[i];
+             MM[i] = (v != NEG) && (v == m);
+           },
+           T1);
   for (int round = 0; round < 2; ++round) {
-    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) T2[i] = MM[i] ? 1.f : 0.f;
-    __syncthreads();
-    maxpool9_inplace(T2, T1);
-    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
-      const bool sp = T2[i] > 0.f;
-      SUPP[i] = sp;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
-      const float v = S[i];
-      T2[i] = (v == NEG) ? NEG : (SUPP[i] ? 0.f : v);
-    }
-    __syncthreads();
-    maxpool9_inplace(T2, T1);
-    for (int i = threadIdx.x; i < NMS_RN; i += blockDim.x) {
-      const float v = S[i];
-      if (v != NEG) {
-        const float ss = SUPP[i] ? 0.f : v;
-        if (ss == T2[i] && !SUPP[i]) MM[i] = 1;
-      }
-    }
-    __syncthreads();
+    maxpool9([&](int i) { return MM[i] ? 1.f : 0.f; }, [&](int i, float m) { SUPP[i] = m > 0.f; }, T1);
+    maxpool9(
+        [&](int i) {
+          const float v = S[i];
+          return (v == NEG) ? NEG : (SUPP[i] ? 0.f : v);
+        },
+        [&](int i, float m) {
+          const float v = S[i];
+          if (v != NEG && !SUPP[i] && v == m) MM[i] = 1;
+        },
+        T1);
   }
   for (int i = threadIdx.x; i < NMS_TW * NMS_TH; i += blockDim.x) {
     const int ty = i / NMS_TW, tx = i - ty * NMS_TW;
@@ -568,7 +561,7 @@ int sp_init(Engine* e) {
     DV_TRY(plan_gemm(&s->pDb, s->aPD + 256, 512, (int)P8, s->wDb, 256, 256, 256, ed));
   }
   DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  NMS_RN * (3 * 4 + 2)));
+                                  NMS_RN * (2 * 4 + 2)));
   // debug views
   e->dbg["gray"] = {s->gray, (int64_t)H * W, 0};
   e->dbg[s->use_halo ? "conv1a_blocked" : "conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
@@ -636,7 +629,7 @@ static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
   SpNet* s = e->sp;
   const int H8 = s->H8, W8 = s->W8, K = e->cfg.max_kpts;
   DV_CUDA_OK(cudaMemsetAsync(s->cand_cnt, 0, sizeof(int) * b, e->st));
-  k_nms_select<<<dim3(cdiv(W8, NMS_TW), cdiv(H8, NMS_TH), b), NMS_THREADS, NMS_RN * (3 * 4 + 2), e->st>>>(
+  k_nms_select<<<dim3(cdiv(W8, NMS_TW), cdiv(H8, NMS_TH), b), NMS_THREADS, NMS_RN * (2 * 4 + 2), e->st>>>(
       smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
   k_topk<<<b, 1024, 0, e->st>>>(s->cand, s->cand_cnt, H8 * W8, K, W8, s->kpts, s->kpts_f, s->scores, s->n_kpts);
   DV_CUDA_OK(cudaGetLastError());
