@@ -264,6 +264,18 @@ class Engine:
                               int(relu), _ptr(D, C.c_float)))
         return D
 
+    def dbg_gemm_ex(self, A, B, bias=None, res=None, res_is_f16=False, relu=False, want32=True, want16=False):
+        A, B = _f32(A), _f32(B)
+        M, K = A.shape; N = B.shape[0]
+        D32 = np.zeros((M, N), np.float32) if want32 else None
+        D16 = np.zeros((M, N), np.float32) if want16 else None
+        bp = _f32(bias) if bias is not None else None
+        rp = _f32(res) if res is not None else None
+        _chk(_lib.dv_dbg_gemm_ex(self._h, _ptr(A, C.c_float), _ptr(B, C.c_float), _ptr(bp, C.c_float),
+                                 _ptr(rp, C.c_float), int(res_is_f16), M, N, K, int(relu), _ptr(D32, C.c_float),
+                                 _ptr(D16, C.c_float)))
+        return D32, D16
+
     def dbg_conv3x3(self, x_nhwc, w_oihw, bias=None, relu=False, pool=False):
         x, w = _f32(x_nhwc), _f32(w_oihw)
         n, h, wd, cin = x.shape; cout = w.shape[0]

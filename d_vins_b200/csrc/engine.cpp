@@ -236,6 +236,67 @@ dv_status dv_dbg_gemm(dv_engine* h, const float* A, const float* Bm, const float
   return (dv_status)rc;
 }
 
+dv_status dv_dbg_gemm_ex(dv_engine* h, const float* A, const float* Bm, const float* bias, const float* res,
+                         int32_t res_is_f16, int32_t M, int32_t N, int32_t K, int32_t relu, float* D32, float* D16) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!A || !Bm || (!D32 && !D16) || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 8)) {
+    set_error("dv_dbg_gemm_ex: need K % 8 == 0, N % 8 == 0 and at least one output");
+    return DV_ERR_INVALID;
+  }
+  const size_t mk = (size_t)M * K, nk = (size_t)N * K, mn = (size_t)M * N;
+  float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr, *dbias = nullptr, *dtmp = nullptr;
+  __half *dA = nullptr, *dB = nullptr, *dD16 = nullptr, *dR16 = nullptr;
+  DV_CUDA_OK(cudaMalloc(&dA32, mk * 4));
+  DV_CUDA_OK(cudaMalloc(&dB32, nk * 4));
+  DV_CUDA_OK(cudaMalloc(&dA, mk * 2));
+  DV_CUDA_OK(cudaMalloc(&dB, nk * 2));
+  DV_CUDA_OK(cudaMalloc(&dD, mn * 4));
+  DV_CUDA_OK(cudaMalloc(&dtmp, mn * 4));
+  DV_CUDA_OK(cudaMalloc(&dD16, mn * 2));
+  DV_CUDA_OK(cudaMalloc(&dR16, mn * 2));
+  DV_CUDA_OK(cudaMemcpyAsync(dA32, A, mk * 4, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dB32, Bm, nk * 4, cudaMemcpyHostToDevice, e->st));
+  if (bias) {
+    DV_CUDA_OK(cudaMalloc(&dbias, (size_t)N * 4));
+    DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice, e->st));
+  }
+  f32_to_f16(dA32, dA, (int64_t)mk, e->st);
+  f32_to_f16(dB32, dB, (int64_t)nk, e->st);
+  EpiParams ep;
+  ep.bias = dbias; ep.relu = relu;
+  if (D32) { ep.out32 = dD; ep.ld32 = N; }
+  if (D16) { ep.out16 = dD16; ep.ld16 = N; }
+  if (res) {
+    if (res_is_f16) {
+      DV_CUDA_OK(cudaMemcpyAsync(dtmp, res, mn * 4, cudaMemcpyHostToDevice, e->st));
+      f32_to_f16(dtmp, dR16, (int64_t)mn, e->st);
+      ep.res16 = dR16; ep.ldr16 = N;
+    } else {
+      // fp32 residual: in place in the output buffer when there is an fp32 output (LightGlue's x += ffn(x))
+      float* r = D32 ? dD : dtmp;
+      DV_CUDA_OK(cudaMemcpyAsync(r, res, mn * 4, cudaMemcpyHostToDevice, e->st));
+      ep.res32 = r; ep.ldr32 = N;
+    }
+  }
+  GemmPlan pl;
+  int rc = plan_gemm(&pl, dA, K, M, dB, K, N, K, ep);
+  if (!rc) rc = launch_gemm(pl, M, e->st);
+  if (!rc) {
+    cudaError_t ce = cudaSuccess;
+    if (D32) ce = cudaMemcpyAsync(D32, dD, mn * 4, cudaMemcpyDeviceToHost, e->st);
+    if (D16 && ce == cudaSuccess) {
+      f16_to_f32(dD16, dtmp, (int64_t)mn, e->st);
+      ce = cudaMemcpyAsync(D16, dtmp, mn * 4, cudaMemcpyDeviceToHost, e->st);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    if (ce != cudaSuccess) { set_error(std::string("dv_dbg_gemm_ex: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
+  }
+  cudaFree(dA32); cudaFree(dB32); cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dbias); cudaFree(dtmp);
+  cudaFree(dD16); cudaFree(dR16);
+  return (dv_status)rc;
+}
+
 dv_status dv_dbg_conv3x3(dv_engine* h, const float* x, const float* wgt, const float* bias, int32_t n, int32_t hh,
                          int32_t ww, int32_t cin, int32_t cout, int32_t relu, int32_t pool, float* y) {
   DV_CHECK_ENGINE(h);

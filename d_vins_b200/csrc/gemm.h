@@ -50,6 +50,11 @@ struct GemmPlan {
   GemmParams p;
   int bn = 0;           // 64 or 128
   int rows_cap = 0;     // plain: max M; conv: max images
+  // staged epilogue (gemm_staged.cu): outputs / residuals move through shared memory with TMA.  The output maps are
+  // encoded for the exact row count of a launch (TMA clips the last tile) and cached until it changes.
+  int staged = 0;
+  mutable CUtensorMap tmO16, tmO32, tmR16, tmR32;
+  mutable int staged_rows = -1;
 };
 
 // A [M_cap, K] fp16 row-major (row pitch lda elements), B = weights [N, K] fp16 row-major (pitch ldb).
@@ -66,6 +71,12 @@ int launch_gemm_batched(const GemmPlan& pl, const int4* desc, int count, int max
 int gemm_init();      // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                     const uint32_t* box, bool swizzle128);
+// 2-D row-major [rows, cols] map of 2- or 4-byte elements, SWIZZLE_128B boxes of box_cols x box_rows
+int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long cols, long rows, long pitch_bytes,
+                     int box_cols, int box_rows);
+bool gemm_staged_eligible(const GemmPlan& pl);
+int gemm_staged_init();
+int launch_gemm_staged(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
 
 // ---- weights-stationary halo-tile 3x3 convolution, 64 -> 64 channels (conv_halo.cu) -------------------------------
 // Activations in the channel-blocked layout [N][C/8][H][W][8] ("NC/8HWC8"): one TMA box per 16x8-pixel output tile

@@ -228,6 +228,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_tmapEncodeTiled g_encode = nullptr;
 static bool g_use_persistent = true;
+static bool g_use_staged = true;
 bool gemm_is_persistent() { return g_use_persistent; }
 int gemm_persistent_init();                                                                    // gemm_persistent.cu
 int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
@@ -250,8 +251,12 @@ int gemm_init() {
   {
     const char* env = getenv("DV_GEMM_PERSISTENT");      // debug toggle: 0 = one tile per CTA (original kernel)
     g_use_persistent = !(env && env[0] == '0');
+    env = getenv("DV_GEMM_STAGED");                       // debug toggle: 0 = register epilogue for every GEMM
+    g_use_staged = !(env && env[0] == '0');
   }
   int rc = gemm_persistent_init();
+  if (rc) return rc;
+  rc = gemm_staged_init();
   if (rc) return rc;
   return conv_halo_init();
 }
@@ -276,6 +281,31 @@ int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t*
   if (r != CUDA_SUCCESS) {
     char b[256];
     snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d) rank %d", (int)r, rank);
+    set_error(b);
+    return DV_ERR_CUDA;
+  }
+  return DV_OK;
+}
+
+int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long cols, long rows, long pitch_bytes,
+                     int box_cols, int box_rows) {
+  if (!g_encode || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0 ||
+      box_cols * elem_bytes != 128) {
+    set_error("tmap_encode_rows: base / pitch must be 16-byte aligned and the box 128 bytes wide");
+    return DV_ERR_INVALID;
+  }
+  cuuint64_t d[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t st[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t bx[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encode(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                        const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[256];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled (rows map) failed (%d): cols %ld rows %ld pitch %ld", (int)r, cols,
+             rows, pitch_bytes);
     set_error(b);
     return DV_ERR_CUDA;
   }
@@ -335,6 +365,8 @@ int plan_gemm(GemmPlan* pl, const __half* A, int lda, int M_cap, const __half* B
   cuuint32_t box[2] = {64, 128};
   int rc = encode(&pl->tmA, A, 2, dims, strides, box);
   if (rc) return rc;
+  pl->staged = g_use_persistent && g_use_staged && gemm_staged_eligible(*pl);
+  pl->staged_rows = -1;
   return encode_weights(pl, B, ldb, N, K);
 }
 
@@ -387,6 +419,7 @@ int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st) {
     p.M = rows;
     m_tiles = cdiv(rows, 128);
   }
+  if (pl.staged) return launch_gemm_staged(pl, p, m_tiles, st);
   if (g_use_persistent) return launch_gemm_persistent(pl, p, m_tiles, st);
   const long grid = m_tiles * p.n_tiles;
   if (pl.bn == 64)

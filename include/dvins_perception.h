@@ -164,6 +164,11 @@ dv_status dv_probe_read(dv_engine* e, double* ms, int64_t* launches, int32_t res
 /* D[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (relu?) : fp32 host in/out, fp16 operands, fp32 accumulate on tcgen05. */
 dv_status dv_dbg_gemm(dv_engine* e, const float* A, const float* B, const float* bias, int32_t M, int32_t N, int32_t K,
                       int32_t relu, float* D);
+/* Same GEMM with the other fused-epilogue operands: an optional residual [M,N] (fp32 - added in place in the fp32
+ * output buffer, as LightGlue's x += ffn(x) does - or rounded to fp16 when res_is_f16), and fp32 and / or fp16 outputs
+ * (D16 is returned widened to fp32).  N % 8 == 0.  Either output may be NULL, not both. */
+dv_status dv_dbg_gemm_ex(dv_engine* e, const float* A, const float* B, const float* bias, const float* res,
+                         int32_t res_is_f16, int32_t M, int32_t N, int32_t K, int32_t relu, float* D32, float* D16);
 /* 3x3 pad-1 conv on NHWC fp16 via the implicit-GEMM tcgen05 kernel: x [n,h,w,cin], wgt [cout,cin,3,3] (torch
  * layout), y [n,h',w',cout] with h' = pool ? h/2 : h. */
 dv_status dv_dbg_conv3x3(dv_engine* e, const float* x, const float* wgt, const float* bias, int32_t n, int32_t h,

@@ -70,3 +70,30 @@ def test_conv3x3_halo64(eng, n, h, w, pool, blocked):
     assert y.shape == ref.shape
     err = np.abs(y - ref).max()
     assert err < 4e-3, err
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 512), (300, 512, 256), (77, 768, 256), (5000, 192, 64),
+                                   (129, 136, 128), (4099, 1024, 320)])
+@pytest.mark.parametrize("mode", ["o16", "o32", "res32_o32_o16", "res16_relu_o16", "res32_o16"])
+def test_gemm_fused_epilogues(eng, M, N, K, mode):
+    """Every epilogue operand of the staged (TMA in / TMA out) kernel: fp16 / fp32 outputs, in-place fp32 residual,
+    fp16 residual + ReLU; ragged M, N not a multiple of the 128 / 64 / 32-column boxes."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K + len(mode))
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32) if "res" in mode else None
+    r16 = "res16" in mode
+    relu = "relu" in mode
+    D32, D16 = eng.dbg_gemm_ex(A, B, bias, res=res, res_is_f16=r16, relu=relu, want32="o32" in mode,
+                               want16="o16" in mode)
+    ref = _q(A).astype(np.float64) @ _q(B).astype(np.float64).T + bias
+    if res is not None:
+        ref = ref + (_q(res) if r16 else res)
+    if relu:
+        ref = np.maximum(ref, 0)
+    if D32 is not None:
+        assert np.abs(D32 - ref).max() < 2e-3
+    if D16 is not None:
+        # one fp16 rounding of the fp32 result
+        assert np.abs(D16 - ref).max() < 2e-3 + np.abs(ref).max() * 2.0 ** -10
