@@ -497,8 +497,16 @@ __global__ void __launch_bounds__(1024) k_lg_extract(const PairDesc* __restrict_
       const float sw1 = (float)(s1.w / 2), sh1 = (float)(s1.h / 2), sc1 = fmaxf(sw1, sh1);
       const float x0 = kpts[(int64_t)(p.off0 + i) * 2], y0 = kpts[(int64_t)(p.off0 + i) * 2 + 1];
       const float x1 = kpts[(int64_t)(p.off1 + j) * 2], y1 = kpts[(int64_t)(p.off1 + j) * 2 + 1];
-      mk0[o * 2] = __fdiv_rn(x0 - sw0, sc0) * sc0 + sw0; mk0[o * 2 + 1] = __fdiv_rn(y0 - sh0, sc0) * sc0 + sh0;
-      mk1[o * 2] = __fdiv_rn(x1 - sw1, sc1) * sc1 + sw1; mk1[o * 2 + 1] = __fdiv_rn(y1 - sh1, sc1) * sc1 + sh1;
+      // the reference's three kernels in sequence, IEEE op by op (no FMA contraction): normalize_kpts (:52-65),
+      // recover_normkpts (:104-137: kn * scale + shift), kpts_post_process (:68-101: (v + .5f) / s - .5f with
+      // s = width_adj / width = 1 under the equal-size precondition).  Pinned by tests/test_refpre_gpu.py.
+      auto rec = [](float v, float sh, float sc) {
+        const float kn = __fdiv_rn(__fsub_rn(v, sh), sc);
+        const float px = __fadd_rn(__fmul_rn(kn, sc), sh);
+        return __fsub_rn(__fdiv_rn(__fadd_rn(px, 0.5f), 1.0f), 0.5f);
+      };
+      mk0[o * 2] = rec(x0, sw0, sc0); mk0[o * 2 + 1] = rec(y0, sh0, sc0);
+      mk1[o * 2] = rec(x1, sw1, sc1); mk1[o * 2 + 1] = rec(y1, sh1, sc1);
     }
     __syncthreads();
     if (tid == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wsum[w]; base_s = base + tot; }

@@ -54,7 +54,10 @@ __global__ void k_gray(const uint8_t* __restrict__ img, float* __restrict__ out,
   } else {
     const float b = (float)img[i * 3 + 0], g = (float)img[i * 3 + 1], r = (float)img[i * 3 + 2];
     const float c0 = __fmul_rn(r, a), c1 = __fmul_rn(g, a), c2 = __fmul_rn(b, a);
-    out[i] = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, c0), __fmul_rn(0.587f, c1)), __fmul_rn(0.114f, c2));
+    // preprocess_kernel.cu:280 writes `0.299 * c0 + 0.587 * c1 + 0.114 * c2` with DOUBLE literals: the mix is evaluated
+    // in fp64 and rounded to fp32 once (pinned against the compiled reference kernel, tests/test_refpre_gpu.py).
+    out[i] = (float)__dadd_rn(__dadd_rn(__dmul_rn(0.299, (double)c0), __dmul_rn(0.587, (double)c1)),
+                              __dmul_rn(0.114, (double)c2));
   }
 }
 

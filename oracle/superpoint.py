@@ -31,13 +31,16 @@ def preprocess_gray(img_u8: np.ndarray) -> np.ndarray:
     precondition): the affine is the identity, bilinear weights are exactly (1,0,0,0), the
     ``floorf(v+0.5f)`` re-quantisation is a no-op, so the result is ``u8 * (1/255.f)``
     (deep_net.cpp:578: a *multiply* by the rounded reciprocal).  3-channel input: BGR->RGB swap
-    ("Invert") then gray = 0.299*c0 + 0.587*c1 + 0.114*c2 (preprocess_kernel.cu:257-260, :280)."""
+    ("Invert") then gray = 0.299*c0 + 0.587*c1 + 0.114*c2 in fp64 (preprocess_kernel.cu:257-260, :280)."""
     a = np.float32(1.0) / np.float32(255.0)
     if img_u8.ndim == 3 and img_u8.shape[2] == 3:
         c = img_u8.astype(np.float32)
         b, g, r = c[..., 0], c[..., 1], c[..., 2]
         c0, c1, c2 = r * a, g * a, b * a        # Invert: c0<->c2 then alpha/beta per channel
-        return (np.float32(0.299) * c0 + np.float32(0.587) * c1 + np.float32(0.114) * c2).astype(np.float32)
+        # preprocess_kernel.cu:280: DOUBLE literals -> the mix is evaluated in fp64, rounded to fp32 once (pinned against
+        # the compiled reference kernel on the GPU: tests/test_refpre_gpu.py)
+        return (0.299 * c0.astype(np.float64) + 0.587 * c1.astype(np.float64)
+                + 0.114 * c2.astype(np.float64)).astype(np.float32)
     return img_u8.astype(np.float32) * a
 
 

@@ -94,3 +94,88 @@ def test_synthetic_stream_revisits():
     assert st.offset(0) == st.offset(10)
     a, b = st.frame(0), st.frame(10)
     assert np.abs(a.astype(int) - b.astype(int)).mean() < 4      # same view, fresh noise
+
+
+def test_lightglue_oracle_matches_hf_golden(all_weights):
+    """tests/golden/lg_hf.npz was produced by HF transformers' LightGlue (an independent port of cvg/LightGlue) with
+    the same synthetic weights (tests/golden/make_golden_lg_hf.py): pairs bit-exact, scores / descriptors to fp32
+    round-off, for M == N, ragged M < N (HF padding mask) and the D_VINS window-vs-keyframe shape."""
+    from oracle import lightglue as olg, weights
+    wl = weights.sub(all_weights, "lg.")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lg_hf.npz"))
+    h, w = int(g["h"]), int(g["w"])
+    for tag in ("equal", "ragged", "window"):
+        keep = {}
+        m, s = olg.lightglue(wl, g[tag + "_k0"], g[tag + "_k1"], g[tag + "_d0"], g[tag + "_d1"], h, w, h, w, keep=keep)
+        assert len(g[tag + "_matches"]) > 0
+        assert np.array_equal(m, g[tag + "_matches"]), tag
+        assert np.abs(s - g[tag + "_mscores"]).max() < 2e-4
+        assert np.abs(keep["x0_8"] - g[tag + "_x0"]).max() < 5e-5
+        assert np.abs(keep["x1_8"] - g[tag + "_x1"]).max() < 5e-5
+
+
+def test_lightglue_oracle_matches_hf_live(all_weights):
+    """Same comparison with the HF model executed in this process (skipped where transformers is not importable)."""
+    pytest.importorskip("transformers")
+    import importlib.util
+    from oracle import lightglue as olg, weights
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_lg_hf", os.path.join(os.path.dirname(__file__), "golden", "make_golden_lg_hf.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    wl = weights.sub(all_weights, "lg.")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lg_hf.npz"))
+    h, w = int(g["h"]), int(g["w"])
+    hf = mk.hf_model(wl)
+    rng = np.random.default_rng(11)
+    k0 = g["ragged_k0"] + rng.uniform(-2, 2, g["ragged_k0"].shape).astype(np.float32)   # a case NOT in the fixture
+    k1, d0, d1 = g["ragged_k1"], g["ragged_d0"], g["ragged_d1"]
+    m0, s0, _, _ = mk.run_hf(hf, k0, k1, d0, d1, h, w)
+    valid = np.nonzero(m0 >= 0)[0]
+    m, s = olg.lightglue(wl, k0, k1, d0, d1, h, w, h, w)
+    assert np.array_equal(m, np.stack([valid, m0[valid]], 1))
+    assert np.abs(s - s0[valid]).max() < 2e-4
+
+
+def test_mixvpr_backbone_matches_torchvision(all_weights):
+    """MixVPR's trunk is torchvision ResNet-50 cropped before layer4 (reference README.md:35-45): the oracle's
+    restatement must equal torchvision's own module loaded with the same state_dict."""
+    tv = pytest.importorskip("torchvision")
+    import torch
+    from oracle import mixvpr as omix, synth, weights
+    wm = weights.sub(all_weights, "mix.")
+    net = tv.models.resnet50(weights=None).eval()
+    sd = {k[len("backbone.model."):]: torch.from_numpy(v) for k, v in wm.items() if k.startswith("backbone.model.")}
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected
+    assert all(k.startswith(("layer4.", "fc.")) or k.endswith("num_batches_tracked") for k in missing), missing
+    x = torch.from_numpy(omix.preprocess_mix(synth.make_frame(480, 752, synth.BASE_SEED)))[None]
+    with torch.no_grad():
+        y = net.layer3(net.layer2(net.layer1(net.maxpool(net.relu(net.bn1(net.conv1(x)))))))
+        o = omix.backbone(wm, x)
+    assert o.shape == (1, 1024, 20, 20)
+    assert torch.equal(o, y) or float((o - y).abs().max()) < 1e-5 * float(y.abs().max())
+
+
+def test_knn_matches_torch_topk():
+    """faiss IndexFlatIP (keyframe.cpp:302-314) = exact inner-product top-k; cross-check the oracle against torch."""
+    import torch
+    from oracle import knn, synth
+    bank, q = synth.make_bank(3000, seed=5)
+    D, I = knn.knn_ip(bank, q, 2500)
+    Dt, It = torch.topk(torch.from_numpy(bank[:2500]) @ torch.from_numpy(q), 3)
+    assert np.array_equal(I, It.numpy())
+    assert np.abs(D - Dt.numpy()).max() < 1e-5
+
+
+def test_mix_preprocess_matches_compiled_reference_golden():
+    """tests/golden/refpre_mix.npz: outputs of the REFERENCE's own warp_affine_bilinear_and_normalize_plane_kernel_mix
+    (preprocess_kernel.cu:348-435, compiled from /root/reference with IEEE flags and run on a B200 by
+    tests/test_refpre_gpu.py).  The oracle's numpy restatement reproduces them bit for bit; the reference's shipped
+    --use_fast_math build differs from both by one u8 level on the recorded (< 0.02 %) positions."""
+    from oracle import mixvpr as omix
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refpre_mix.npz"))
+    for tag in ("euroc", "noise"):
+        o = omix.preprocess_mix(g[tag + "_img"])
+        assert np.array_equal(o, g[tag + "_ieee"])
+        assert len(g[tag + "_fast_levels_diff"]) < 2e-3 * o.size
