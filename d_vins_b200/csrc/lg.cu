@@ -16,6 +16,11 @@
 namespace dv {
 
 static constexpr int LG_D = 256, LG_HEADS = 4, LG_LAYERS = 9;
+// Token segments (one per image) are packed back to back, each padded to LG_SEGPAD rows only: the row-wise kernels
+// (GEMMs, LayerNorm) do not care about segment boundaries, the attention / assignment kernels bound every access by
+// the segment's own (off, n).  (Padding to the 128-row GEMM tile, as before, cost 26 % extra rows at 150 + 662 tokens.)
+static constexpr int LG_SEGPAD = 16;
+__host__ __device__ static inline int lg_pad(int n) { return (n + LG_SEGPAD - 1) & ~(LG_SEGPAD - 1); }
 
 struct AttnJob {
   const __half* q; const __half* k; const __half* v; __half* o;
@@ -74,7 +79,7 @@ __global__ void k_lg_load(const LgSeg* __restrict__ segs, const float* __restric
                           __half* __restrict__ X2, float* __restrict__ cs, float* __restrict__ sn,
                           float* __restrict__ kpts_out) {
   const LgSeg sg = segs[blockIdx.y];
-  const int rows = (sg.n + 127) & ~127;
+  const int rows = lg_pad(sg.n);
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps) {
     const int64_t t = sg.off + r;
@@ -706,7 +711,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     hs[i] = segs_in[i];
     if (hs[i].n < 1 || hs[i].n > e->cfg.lg_max_kpts) { set_error("lg_run: keypoint count out of range"); return DV_ERR_INVALID; }
     hs[i].off = off;
-    off += (hs[i].n + 127) & ~127;
+    off += lg_pad(hs[i].n);
     max_n_any = std::max(max_n_any, hs[i].n);
   }
   const int T = off;
