@@ -55,6 +55,7 @@ template <bool FUSE1A>
 __global__ void __launch_bounds__(FUSE1A ? 320 + 32 * NPROD : 320, 1)
 conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const HaloParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -81,11 +82,14 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (warp != 0) pdl_wait();
 
   if (warp == 0) {
     if (elect_one_sync()) {
+      // the 72 KB of filter taps are constants: their load overlaps the previous kernel's tail (PDL), then wait
       mbar_arrive_expect_tx(w_bar, W_BYTES);
       for (int t = 0; t < 9; ++t) tma_load_2d(smem + OFF_W + t * 8192, &tmW, w_bar, t * 64, 0);
+      pdl_wait();
       int it = 0;
       if (!FUSE1A)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -294,9 +298,9 @@ int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st) {
   p.gray = pl.gray; p.w1a = pl.w1a; p.b1a = pl.b1a;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
   if (pl.gray)
-    conv3x3_halo64_kernel<true><<<grid, 320 + 32 * NPROD, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
+    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<true>, dim3(grid), dim3(320 + 32 * NPROD), SMEM_BYTES, st, pl.tmX, pl.tmW, p));
   else
-    conv3x3_halo64_kernel<false><<<grid, 320, SMEM_BYTES, st>>>(pl.tmX, pl.tmW, p);
+    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<false>, dim3(grid), dim3(320), SMEM_BYTES, st, pl.tmX, pl.tmW, p));
   DV_CUDA_OK(cudaGetLastError());
   return DV_OK;
 }

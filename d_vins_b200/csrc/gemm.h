@@ -77,6 +77,10 @@ int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long col
 bool gemm_staged_eligible(const GemmPlan& pl);
 int gemm_staged_init();
 int launch_gemm_staged(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
+// weights-resident variant for K <= 512 (gemm_wres.cu): a CTA keeps a 128/256-column slab of W in shared memory
+bool gemm_wres_eligible(const GemmPlan& pl, long m_tiles);
+int gemm_wres_init();
+int launch_gemm_wres(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
 
 // ---- weights-stationary halo-tile 3x3 convolution, 64 -> 64 channels (conv_halo.cu) -------------------------------
 // Activations in the channel-blocked layout [N][C/8][H][W][8] ("NC/8HWC8"): one TMA box per 16x8-pixel output tile

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const GemmParams p, const int m_tiles) {
   using C = PCfg<BN>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();      // prologue above reads only weights (bias); activations / batch descriptors from here on
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -356,9 +358,11 @@ int launch_gemm_persistent(const GemmPlan& pl, const GemmParams& p, long m_tiles
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st);
   }
   if (pl.bn == 64)
-    umma_gemm_persist_kernel<64><<<grid, 320, PCfg<64>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pp, (int)m_tiles);
+    DV_CUDA_OK(launch_pdl(umma_gemm_persist_kernel<64>, dim3(grid), dim3(320), PCfg<64>::SMEM_BYTES, st, pl.tmA, pl.tmB, pp,
+                          (int)m_tiles));
   else
-    umma_gemm_persist_kernel<128><<<grid, 320, PCfg<128>::SMEM_BYTES, st>>>(pl.tmA, pl.tmB, pp, (int)m_tiles);
+    DV_CUDA_OK(launch_pdl(umma_gemm_persist_kernel<128>, dim3(grid), dim3(320), PCfg<128>::SMEM_BYTES, st, pl.tmA, pl.tmB, pp,
+                          (int)m_tiles));
   DV_CUDA_OK(cudaGetLastError());
   if (want_dbg) {
     long long h[8];

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(320, 1)
                             const __grid_constant__ CUtensorMap tmR32, const __grid_constant__ CUtensorMap tmR16,
                             const GemmParams p, const int m_tiles) {
   using C = SCfg<F32, F16>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(320, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();      // everything above touched only weights / on-chip state; operands of earlier kernels from here on
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -315,14 +317,14 @@ int launch_gemm_staged(const GemmPlan& pl, const GemmParams& p, long m_tiles, cu
   const int grid = (int)(total < g_sms_staged ? total : g_sms_staged);
   const bool f32 = ep.out32 || ep.res32, f16 = ep.out16 || ep.res16;
   if (f32 && f16)
-    umma_gemm_staged_kernel<true, true><<<grid, 320, SCfg<true, true>::SMEM_BYTES, st>>>(
-        pl.tmA, pl.tmB, pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, p, (int)m_tiles);
+    DV_CUDA_OK(launch_pdl(umma_gemm_staged_kernel<true, true>, dim3(grid), dim3(320), SCfg<true, true>::SMEM_BYTES, st,
+                          pl.tmA, pl.tmB, pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, p, (int)m_tiles));
   else if (f32)
-    umma_gemm_staged_kernel<true, false><<<grid, 320, SCfg<true, false>::SMEM_BYTES, st>>>(
-        pl.tmA, pl.tmB, pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, p, (int)m_tiles);
+    DV_CUDA_OK(launch_pdl(umma_gemm_staged_kernel<true, false>, dim3(grid), dim3(320), SCfg<true, false>::SMEM_BYTES, st,
+                          pl.tmA, pl.tmB, pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, p, (int)m_tiles));
   else
-    umma_gemm_staged_kernel<false, true><<<grid, 320, SCfg<false, true>::SMEM_BYTES, st>>>(
-        pl.tmA, pl.tmB, pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, p, (int)m_tiles);
+    DV_CUDA_OK(launch_pdl(umma_gemm_staged_kernel<false, true>, dim3(grid), dim3(320), SCfg<false, true>::SMEM_BYTES, st,
+                          pl.tmA, pl.tmB, pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, p, (int)m_tiles));
   DV_CUDA_OK(cudaGetLastError());
   return DV_OK;
 }

@@ -258,6 +258,8 @@ int gemm_init() {
   if (rc) return rc;
   rc = gemm_staged_init();
   if (rc) return rc;
+  rc = gemm_wres_init();
+  if (rc) return rc;
   return conv_halo_init();
 }
 
@@ -419,7 +421,27 @@ int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st) {
     p.M = rows;
     m_tiles = cdiv(rows, 128);
   }
-  if (pl.staged) return launch_gemm_staged(pl, p, m_tiles, st);
+  static const bool want_time = getenv("DV_GEMM_TIME") != nullptr;   // diagnostics: per-launch event timing to stderr
+  if (want_time && !p.conv) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const bool wres = pl.staged && gemm_wres_eligible(pl, m_tiles);
+    cudaEventRecord(e0, st);
+    int rc = wres ? launch_gemm_wres(pl, p, m_tiles, st)
+                  : (pl.staged ? launch_gemm_staged(pl, p, m_tiles, st) : launch_gemm_persistent(pl, p, m_tiles, st));
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[gemm time] M %d N %d K %d %s: %.1f us = %.0f TFLOP/s\n", p.M, p.N, p.K,
+            wres ? "wres" : (pl.staged ? "staged" : "persist"), ms * 1e3, 2.0 * p.M * p.N * p.K / (ms * 1e-3) / 1e12);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+  }
+  if (pl.staged) {
+    if (gemm_wres_eligible(pl, m_tiles)) return launch_gemm_wres(pl, p, m_tiles, st);
+    return launch_gemm_staged(pl, p, m_tiles, st);
+  }
   if (g_use_persistent) return launch_gemm_persistent(pl, p, m_tiles, st);
   const long grid = m_tiles * p.n_tiles;
   if (pl.bn == 64)

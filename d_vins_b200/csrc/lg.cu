@@ -152,6 +152,8 @@ __global__ void __launch_bounds__(128) k_lg_attention(const AttnJob* __restrict_
   __shared__ __align__(16) __half sQ[64 * ATT_LD];
   __shared__ __align__(16) __half sKb[2][64 * ATT_LD];   // double-buffered K / V chunks (cp.async)
   __shared__ __align__(16) __half sVb[2][64 * ATT_LD];
+  pdl_trigger();
+  pdl_wait();
   const AttnJob jb = jobs[blockIdx.z];
   const int q0 = blockIdx.x * 64;
   if (q0 >= jb.nq) return;
@@ -302,6 +304,8 @@ __global__ void __launch_bounds__(128) k_lg_attention(const AttnJob* __restrict_
 // LayerNorm(512, eps 1e-5, affine) + exact (erf) GELU, fp32 in -> fp16 out.  One warp per token.
 __global__ void k_lg_ln_gelu(const __half* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                              __half* __restrict__ out, int64_t T) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (t >= T) return;
@@ -750,25 +754,27 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     if (!gemm_is_persistent())
       k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
     if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_self, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-    else k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_self, 0.125f);
+    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(128), 0, e->st, (const AttnJob*)g->jobs_self, 0.125f));
     DV_TRY(launch_gemm(L.p_out, T, e->st));
     if (g->fused_ffn) {
       DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
     } else {
       DV_TRY(launch_gemm(L.p_f0, T, e->st));
-      k_lg_ln_gelu<<<cdiv(T, 8), 256, 0, e->st>>>(g->ffh, L.ln_g, L.ln_b, g->ffg, T);
+      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(cdiv(T, 8)), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
+                            (const float*)L.ln_b, g->ffg, (int64_t)T));
       DV_TRY(launch_gemm(L.p_f3, T, e->st));
     }
     // cross block
     DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
     if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_cross, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-    else k_lg_attention<<<agrid, 128, 0, e->st>>>(g->jobs_cross, 0.125f);
+    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(128), 0, e->st, (const AttnJob*)g->jobs_cross, 0.125f));
     DV_TRY(launch_gemm(L.pc_out, T, e->st));
     if (g->fused_ffn) {
       DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
     } else {
       DV_TRY(launch_gemm(L.pc_f0, T, e->st));
-      k_lg_ln_gelu<<<cdiv(T, 8), 256, 0, e->st>>>(g->ffh, L.cln_g, L.cln_b, g->ffg, T);
+      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(cdiv(T, 8)), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
+                            (const float*)L.cln_b, g->ffg, (int64_t)T));
       DV_TRY(launch_gemm(L.pc_f3, T, e->st));
     }
     DV_LAUNCHED(e, 13);

@@ -1,8 +1,14 @@
 #include <algorithm>
+#include <stdlib.h>
 
 #include "engine.h"
 
 namespace dv {
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DV_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 __global__ void k_f32_to_f16(const float* __restrict__ s, __half* __restrict__ d, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

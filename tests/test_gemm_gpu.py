@@ -73,7 +73,10 @@ def test_conv3x3_halo64(eng, n, h, w, pool, blocked):
 
 
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 512), (300, 512, 256), (77, 768, 256), (5000, 192, 64),
-                                   (129, 136, 128), (4099, 1024, 320)])
+                                   (129, 136, 128), (4099, 1024, 320),
+                                   # weights-resident kernel (gemm_wres.cu): 256-column slabs (K <= 256), 128-column
+                                   # slabs (K = 512), several row tiles per CTA, ragged last tile
+                                   (2000, 768, 256), (20001, 256, 256), (1500, 512, 512), (2085, 1024, 128)])
 @pytest.mark.parametrize("mode", ["o16", "o32", "res32_o32_o16", "res16_relu_o16", "res32_o16"])
 def test_gemm_fused_epilogues(eng, M, N, K, mode):
     """Every epilogue operand of the staged (TMA in / TMA out) kernel: fp16 / fp32 outputs, in-place fp32 residual,
