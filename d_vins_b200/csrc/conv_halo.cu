@@ -29,10 +29,18 @@ constexpr int OFF_W = 0;
 constexpr int OFF_HALO = W_BYTES;                   // 73728 (1024-aligned)
 constexpr int OFF_BAR = OFF_HALO + STAGES * HALO_STRIDE;
 constexpr int OFF_BIAS = OFF_BAR + 256;
-constexpr int OFF_GRAY = OFF_BIAS + 256;            // FUSE1A: two (TH+4) x (TW+4) fp32 windows of the gray frame
+constexpr int OFF_GRAY = OFF_BIAS + 512;            // FUSE1A: two (TH+4) x (TW+4) fp32 windows of the gray frame
 constexpr int GRAY_H = TH + 4, GRAY_W = TW + 4;
-constexpr int SMEM_BYTES = OFF_GRAY + 2 * GRAY_H * GRAY_W * 4 + 1024;
-constexpr int NPROD = 8;                            // FUSE1A producer warps (one per output channel group of conv1a)
+constexpr int NPROD = 8;                            // FUSE == 1 producer warps (one per output channel group of conv1a)
+// FUSE == 2 (conv1a on the tensor cores): im2col operand A1 [256 halo-pixel rows x 16 taps] fp16, no-swizzle K-major
+// ([k/8][row][8]: SBO 128 B, LBO 4096 B), double-buffered; W1a' [64 x 16] in the same canonical layout (LBO 1024 B)
+constexpr int OFF_A1 = (OFF_GRAY + 2 * GRAY_H * GRAY_W * 4 + 127) & ~127;
+constexpr int A1_BYTES = 2 * 256 * 16;              // 8192
+constexpr int OFF_W1A = OFF_A1 + 2 * A1_BYTES;
+constexpr int SMEM_BYTES = OFF_W1A + 2048 + 1024;
+constexpr int NMID = 8;                             // FUSE == 2: warps 10-17 move conv1a from TMEM into the halo buffer
+constexpr int NIM2COL = 2;                          // FUSE == 2: warps 18-19 build A1 from the u8 frame
+constexpr int NPIX = HH * HW;                       // 180 halo pixels
 }  // namespace
 
 struct HaloParams {
@@ -44,6 +52,7 @@ struct HaloParams {
   const float* gray;   // [N, H, W] fp32
   const float* w1a;    // [64, 9]
   const float* b1a;    // [64]
+  const uint8_t* img8; // FUSE == 2: the 1-channel u8 frame itself [N, H, W]
 };
 
 // FUSE1A = true: SuperPoint conv1a + conv1b in one kernel.  The 64-channel full-resolution conv1a activation (46 MB per
@@ -51,10 +60,18 @@ struct HaloParams {
 // warps (one per group of 8 output channels, lanes = halo pixels) compute the 18x10x64 halo of conv1a on CUDA cores
 // from a 20x12 window of the gray frame and store it as fp16 in exactly the [c/8][18][10][8] layout the TMA box
 // would have produced; pixels outside the image are zeros (conv1b's zero padding), not conv1a evaluated out of range.
-template <bool FUSE1A>
-__global__ void __launch_bounds__(FUSE1A ? 320 + 32 * NPROD : 320, 1)
+//
+// FUSE == 2: conv1a itself runs on the tensor cores.  Two warps gather each halo pixel's 3x3 neighbourhood from the u8
+// frame into an im2col operand A1 [180 (-> 256) x 16] (u8 / 256 is exact in fp16; the 256/255 lands in the weights),
+// the MMA thread issues D1[256 x 64] = A1 x W1a'^T (two M=128, N=64, K=16 instructions, 64 tensor cycles) one tile
+// ahead of conv1b, four "mid" warps read D1 from TMEM, add the bias, ReLU, convert and store it as the
+// [c/8][18][10][8] fp16 halo of conv1b (zeros outside the image).  ~100 instructions per thread per tile instead of the
+// ~700 of the CUDA-core producer, so the conv1b MMAs stay the critical path.
+template <int FUSE>
+__global__ void __launch_bounds__(FUSE == 1 ? 320 + 32 * NPROD : (FUSE == 2 ? 320 + 32 * (NMID + NIM2COL) : 320), 1)
 conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                       const HaloParams p) {
+  constexpr bool FUSE1A = FUSE == 1;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -63,21 +80,42 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   uint64_t* acc_full = empty + STAGES;
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* w_bar = acc_empty + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* a1_full = w_bar + 1;                   // FUSE == 2: [2] im2col operand built / consumed, D1 ready / drained
+  uint64_t* a1_empty = a1_full + 2;
+  uint64_t* d1_full = a1_empty + 2;
+  uint64_t* d1_empty = d1_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d1_empty + 2);
+  constexpr uint32_t TMEM_COLS = FUSE == 2 ? 512 : 128;   // D2: 2 x 64 columns; FUSE == 2 adds D1: 2 x (2 x 64) at column 128
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], FUSE1A ? NPROD : 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], FUSE1A ? NPROD : (FUSE == 2 ? NMID : 1)); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&a1_full[b], NIM2COL); mbar_init(&a1_empty[b], 1); mbar_init(&d1_full[b], 1); mbar_init(&d1_empty[b], NMID);
+    }
     mbar_init(w_bar, 1);
     fence_barrier_init();
   }
   float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
   if (threadIdx.x >= 64 && threadIdx.x < 128) sbias[threadIdx.x - 64] = p.bias[threadIdx.x - 64];
-  if (warp == 1) tmem_alloc(tmem_ptr, 128);
+  if (FUSE == 2 && threadIdx.x >= 128 && threadIdx.x < 192) sbias[threadIdx.x - 64] = p.b1a[threadIdx.x - 128];   // [64..127]
+  if (FUSE == 2) {
+    // W1a' = w1a * 256/255 as fp16 in the canonical no-swizzle K-major layout; taps 9..15 and A1's spare rows are zero
+    __half* w1 = reinterpret_cast<__half*>(smem + OFF_W1A);
+    for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+      const int n = i >> 4, k = i & 15;
+      const float v = k < 9 ? p.w1a[n * 9 + k] * (256.0f / 255.0f) : 0.f;
+      w1[(k >> 3) * 512 + n * 8 + (k & 7)] = __float2half_rn(v);
+    }
+    uint4* a1z = reinterpret_cast<uint4*>(smem + OFF_A1);
+    for (int i = threadIdx.x; i < 2 * A1_BYTES / 16; i += blockDim.x) a1z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -91,7 +129,7 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       for (int t = 0; t < 9; ++t) tma_load_2d(smem + OFF_W + t * 8192, &tmW, w_bar, t * 64, 0);
       pdl_wait();
       int it = 0;
-      if (!FUSE1A)
+      if (FUSE == 0)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES;
         mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -107,9 +145,26 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       constexpr uint32_t idesc = make_idesc_f16_f32(128, 64);
       mbar_wait(w_bar, 0);
       const uint64_t db_base = make_desc_sw128(smem_u32(smem + OFF_W));
+      // FUSE == 2: conv1a of tile j, D1[b] = A1[b] x W1a'^T, issued one tile ahead of the conv1b MMAs that consume it
+      const uint64_t dw1 = make_desc_noswz(smem_u32(smem + OFF_W1A), 1024, 128);
+      auto issue_conv1a = [&](int j) {
+        const int b = j & 1;
+        mbar_wait(&a1_full[b], (j >> 1) & 1);
+        mbar_wait(&d1_empty[b], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a1 = smem_u32(smem + OFF_A1 + b * A1_BYTES);
+        const uint32_t d1 = tmem_base + 128u + (uint32_t)(b * 128);
+        tc_mma_f16(d1, make_desc_noswz(a1, 4096, 128), dw1, idesc, 0u);
+        tc_mma_f16(d1 + 64u, make_desc_noswz(a1 + 128 * 16, 4096, 128), dw1, idesc, 0u);
+        tc_commit(&a1_empty[b]);
+        tc_commit(&d1_full[b]);
+      };
+      const int my_tiles = ((int)blockIdx.x < p.total_tiles) ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      if (FUSE == 2 && my_tiles > 0) issue_conv1a(0);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, a = it & 1;
+        if (FUSE == 2 && it + 1 < my_tiles) issue_conv1a(it + 1);
         mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
         mbar_wait(&full[s], (it / STAGES) & 1);
         tc_fence_after();
@@ -127,6 +182,106 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tc_commit(&empty[s]);
         tc_commit(&acc_full[a]);
       }
+    }
+  } else if (FUSE == 2 && warp >= 10 && warp < 10 + NMID) {
+    // ------------------------------------------------------------------ mid epilogue: conv1a TMEM -> conv1b halo
+    const int q = warp & 3;                         // TMEM lane quarter
+    const int half = (warp - 10) >> 2;              // 32-channel half of conv1a's 64 outputs
+    float bv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bv[j] = sbias[64 + half * 32 + j];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES, b = it & 1;
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+      mbar_wait(&d1_full[b], (it >> 1) & 1);
+      mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);                // the conv1b MMAs that read this halo slot have retired
+      tc_fence_after();
+      uint8_t* halo = smem + OFF_HALO + s * HALO_STRIDE;
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        if (blk * 128 + q * 32 >= NPIX) continue;                   // warp-uniform
+        const int px = blk * 128 + q * 32 + lane;
+        const int hh = px / HW, ww = px - hh * HW;
+        const int y = th_i * TH - 1 + hh, x = tw_i * TW - 1 + ww;   // image position of this halo pixel
+        const bool inside = px < NPIX && y >= 0 && y < p.H && x >= 0 && x < p.W;
+        {
+          uint32_t rr[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)(b * 128 + blk * 64 + half * 32), rr);
+          tmem_ld_wait();
+          if (px < NPIX) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __align__(16) __half2 hv[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float v0 = fmaxf(__uint_as_float(rr[g * 8 + 2 * j]) + bv[g * 8 + 2 * j], 0.f);
+                const float v1 = fmaxf(__uint_as_float(rr[g * 8 + 2 * j + 1]) + bv[g * 8 + 2 * j + 1], 0.f);
+                hv[j] = inside ? __floats2half2_rn(v0, v1) : __floats2half2_rn(0.f, 0.f);
+              }
+              *reinterpret_cast<uint4*>(halo + (half * 4 + g) * (NPIX * 16) + px * 16) = *reinterpret_cast<const uint4*>(hv);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();             // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive_cnt(&full[s]); mbar_arrive_cnt(&d1_empty[b]); }
+    }
+  } else if (FUSE == 2 && warp >= 10 + NMID) {
+    // ------------------------------------------------------------------ im2col producers: u8 frame -> A1
+    const int pt = threadIdx.x - 32 * (10 + NMID);  // 0..63
+    __half* gbuf = reinterpret_cast<__half*>(smem + OFF_GRAY);
+    constexpr int WPT = (GRAY_H * GRAY_W + 32 * NIM2COL - 1) / (32 * NIM2COL);   // window pixels per thread (4)
+    // the (TH+4) x (TW+4) u8 window of a tile; pixels outside the image are conv1a's own zero padding.  The window of
+    // tile it+1 is fetched into registers while A1 of tile it is built, so the L2 latency stays off the per-tile chain.
+    auto fetch = [&](int tile, float (&v)[WPT]) {
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int th_i = rem / p.tiles_w, tw_i = rem - th_i * p.tiles_w;
+      const int h0 = th_i * TH - 2, w0 = tw_i * TW - 2;
+#pragma unroll
+      for (int j = 0; j < WPT; ++j) {
+        const int i = pt + j * 32 * NIM2COL;
+        const int gy = i / GRAY_W, gx = i - gy * GRAY_W;
+        const int y = h0 + gy, x = w0 + gx;
+        const bool ok = i < GRAY_H * GRAY_W && y >= 0 && y < p.H && x >= 0 && x < p.W;
+        v[j] = ok ? (float)__ldg(p.img8 + ((int64_t)img * p.H + y) * p.W + x) : 0.f;
+      }
+    };
+    float cur[WPT];
+    if ((int)blockIdx.x < p.total_tiles) fetch(blockIdx.x, cur);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int b = it & 1;
+      __half* g = gbuf + b * (GRAY_H * GRAY_W);
+#pragma unroll
+      for (int j = 0; j < WPT; ++j) {
+        const int i = pt + j * 32 * NIM2COL;
+        if (i < GRAY_H * GRAY_W) g[i] = __float2half_rn(cur[j] * (1.0f / 256.0f));      // u8 / 256: exact in fp16
+      }
+      if (tile + (int)gridDim.x < p.total_tiles) fetch(tile + gridDim.x, cur);
+      asm volatile("bar.sync 2, 64;" ::: "memory");                 // window visible to both producer warps
+      mbar_wait(&a1_empty[b], ((it >> 1) & 1) ^ 1);                 // conv1a MMAs of tile it-2 have retired
+      uint8_t* a1 = smem + OFF_A1 + b * A1_BYTES;
+      for (int px = pt; px < NPIX; px += 32 * NIM2COL) {
+        const int hh = px / HW, ww = px - hh * HW;
+        __align__(16) __half v[16];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int q3 = 0; q3 < 3; ++q3) v[r * 3 + q3] = g[(hh + r) * GRAY_W + ww + q3];
+#pragma unroll
+        for (int k = 9; k < 16; ++k) v[k] = __float2half_rn(0.f);
+        *reinterpret_cast<uint4*>(a1 + px * 16) = *reinterpret_cast<const uint4*>(&v[0]);
+        *reinterpret_cast<uint4*>(a1 + 4096 + px * 16) = *reinterpret_cast<const uint4*>(&v[8]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cnt(&a1_full[b]);
     }
   } else if (FUSE1A && warp >= 10) {
     // ------------------------------------------------------------------ conv1a producers (CUDA cores)
@@ -255,7 +410,7 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -263,8 +418,9 @@ conv3x3_halo64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 static int g_num_sms = 148;
 
 int conv_halo_init() {
-  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(conv3x3_halo64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0;
   DV_CUDA_OK(cudaGetDevice(&dev));
   DV_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -295,12 +451,15 @@ int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st) {
   p.H = pl.H; p.W = pl.W; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.total_tiles = n_img * pl.tiles_w * pl.tiles_h;
   p.bias = pl.bias; p.out = pl.out; p.out_blocked = pl.out_blocked; p.relu = pl.relu; p.pool = pl.pool;
-  p.gray = pl.gray; p.w1a = pl.w1a; p.b1a = pl.b1a;
+  p.gray = pl.gray; p.w1a = pl.w1a; p.b1a = pl.b1a; p.img8 = pl.img8;
   const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-  if (pl.gray)
-    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<true>, dim3(grid), dim3(320 + 32 * NPROD), SMEM_BYTES, st, pl.tmX, pl.tmW, p));
+  if (pl.img8)
+    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<2>, dim3(grid), dim3(320 + 32 * (NMID + NIM2COL)), SMEM_BYTES, st, pl.tmX,
+                          pl.tmW, p));
+  else if (pl.gray)
+    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<1>, dim3(grid), dim3(320 + 32 * NPROD), SMEM_BYTES, st, pl.tmX, pl.tmW, p));
   else
-    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<false>, dim3(grid), dim3(320), SMEM_BYTES, st, pl.tmX, pl.tmW, p));
+    DV_CUDA_OK(launch_pdl(conv3x3_halo64_kernel<0>, dim3(grid), dim3(320), SMEM_BYTES, st, pl.tmX, pl.tmW, p));
   DV_CUDA_OK(cudaGetLastError());
   return DV_OK;
 }

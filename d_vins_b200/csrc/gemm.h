@@ -97,6 +97,8 @@ struct HaloPlan {
   const float* gray = nullptr;   // [N,H,W] fp32
   const float* w1a = nullptr;    // [64,9]
   const float* b1a = nullptr;    // [64]
+  // ... or, on the tensor cores, straight from the 1-channel u8 frame (takes precedence over `gray`)
+  const uint8_t* img8 = nullptr; // [N,H,W] u8
 };
 int plan_conv3x3_halo64(HaloPlan* pl, const __half* x_blocked, int n_cap, int H, int W, const __half* w /*[64,576]*/,
                         const float* bias, __half* out, int out_blocked, int relu, int pool);

@@ -25,6 +25,7 @@ struct SpNet {
   GemmPlan p1b, p2a, p2b, p3a, p3b, p4a, p4b, pPD, pPb, pDb;
   HaloPlan h1b, h2a, h2b;                               // weights-stationary halo kernels for the 64->64 layers
   bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
+  int fuse1a_tc = 0;                                    // DV_SP_FUSE1A=2: conv1a on the tensor cores inside conv1b (conv_halo.cu FUSE == 2)
   bool fuse1a = false;                                  // DV_SP_FUSE1A=1: conv1a inside conv1b's producer (correct, but the
                                                         // CUDA-core producer is 3x slower than the tensor main loop - r01)
   // post
@@ -544,7 +545,8 @@ int sp_init(Engine* e) {
   DV_TRY(plan_conv3x3_halo64(&s->h1b, s->a1a, B, H, W, s->w[0], s->bias[0], s->a1b, 1, 1, 1));
   {
     const char* env = getenv("DV_SP_FUSE1A");
-    s->fuse1a = (env && env[0] == '1');
+    s->fuse1a = (env && env[0] == '1');            // 1: CUDA-core conv1a in conv1b's producer (slower; kept for A/B)
+    s->fuse1a_tc = (!env || env[0] == '2') ? 1 : 0;   // default: conv1a on the tensor cores inside conv1b; 0: separate kernel
     if (s->fuse1a) { s->h1b.gray = s->gray; s->h1b.w1a = s->w1a; s->h1b.b1a = s->b1a; }   // conv1a inside conv1b's producer
   }
   DV_TRY(plan_conv3x3_halo64(&s->h2a, s->a1b, B, H2, W2, s->w[1], s->bias[1], s->a2a, 1, 1, 0));
@@ -596,13 +598,22 @@ int sp_run_encoder(Engine* e, int b) {
   const int64_t npix = (int64_t)b * H * W;
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
   if (s->use_halo) {
-    if (!s->fuse1a) {
+    // 1-channel frames: conv1a runs on the tensor cores inside conv1b, straight from the u8 frame (3-channel frames
+    // go through the fp64 gray mix of k_gray and the separate conv1a kernel)
+    const bool tc1a = s->fuse1a_tc && e->img_ch == 1;
+    if (!s->fuse1a && !tc1a) {
       k_conv1a_blocked<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
       DV_CUDA_OK(cudaGetLastError());
     }
     {
       ProbeScope pr(e);
-      DV_TRY(launch_conv_halo64(s->h1b, b, e->st));
+      if (tc1a) {
+        HaloPlan hp = s->h1b;
+        hp.img8 = e->d_img; hp.w1a = s->w1a; hp.b1a = s->b1a;
+        DV_TRY(launch_conv_halo64(hp, b, e->st));
+      } else {
+        DV_TRY(launch_conv_halo64(s->h1b, b, e->st));
+      }
     }
     DV_TRY(launch_conv_halo64(s->h2a, b, e->st));
     DV_TRY(launch_conv_halo64(s->h2b, b, e->st));

@@ -55,7 +55,13 @@ def test_encoder_activations(eng, frame_and_oracle):
     img, o, keep = frame_and_oracle
     eng.frame_upload(img)
     eng.sp_detect()
-    for name, key in (("conv1a", "conv1a"), ("conv2a", "conv2a"), ("conv3a", "conv3a"), ("conv4a", "conv4a"),
+    import torch
+    import torch.nn.functional as F
+    # conv1a runs inside the conv1b kernel (tensor cores, conv_halo.cu FUSE == 2) and never reaches memory: the first
+    # observable activation is conv1b after its fused 2x2 max-pool
+    keep = dict(keep)
+    keep["conv1b_pool"] = F.max_pool2d(torch.as_tensor(keep["conv1b"]), 2, 2)
+    for name, key in (("conv1b_pool", "conv1b_pool"), ("conv2a", "conv2a"), ("conv3a", "conv3a"), ("conv4a", "conv4a"),
                       ("conv4b", "conv4b")):
         ref = parity.nhwc(keep[key])
         try:
@@ -70,6 +76,28 @@ def test_encoder_activations(eng, frame_and_oracle):
     assert np.abs(got - ref).max() < 0.08, np.abs(got - ref).max()
     sm = eng.dbg_read("score_map").reshape(480, 752)
     assert np.abs(sm - o["score_map"]).max() < parity.SCORE_ATOL
+
+
+def test_conv1a_unfused_paths(weights_file, frame_and_oracle, monkeypatch):
+    """DV_SP_FUSE1A=0: separate CUDA-core conv1a kernel (also the path 3-channel frames take); =1: CUDA-core conv1a in
+    conv1b's producer.  Both must agree with the oracle like the default tensor-core fusion does."""
+    from d_vins_b200 import capi
+    img, o, keep = frame_and_oracle
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DV_SP_FUSE1A", mode)
+        e = capi.Engine(height=480, width=752, weights_path=weights_file)
+        try:
+            e.frame_upload(img)
+            e.sp_detect()
+            if mode == "0":
+                ref = parity.nhwc(keep["conv1a"])
+                hh, ww, cc = ref.shape
+                got = e.dbg_read("conv1a_blocked").reshape(cc // 8, hh, ww, 8).transpose(1, 2, 0, 3).reshape(hh, ww, cc)
+                assert np.abs(got - ref).max() < 0.03 * max(1.0, np.abs(ref).max())
+            sm = e.dbg_read("score_map").reshape(480, 752)
+            assert np.abs(sm - o["score_map"]).max() < parity.SCORE_ATOL
+        finally:
+            e.close()
 
 
 def test_superpoint_end_to_end(eng, frame_and_oracle):
