@@ -11,7 +11,8 @@ older keyframe held in the device-resident feature store).
           max over ranks)
   e2e   : the same round through the C ABI with host buffers: pinned-host -> device frame upload and all result
           read-backs inside the timed region
-  roofline : dominant kernel = conv1b implicit GEMM (43 % of SuperPoint's MACs), event pair around every launch
+  roofline : dominant kernel = fused conv1a + conv1b implicit GEMM (44 % of SuperPoint's MACs), event pair around
+             every launch
   cpu_baseline / --impl reference : the CPU oracle (PyTorch fp32 port of the reference's arithmetic) on the host cores
 
 Contract: `python bench.py --gpus N --steps K --warmup W`; under torchrun one rank per GPU.  ONE JSON line on rank 0.
@@ -38,8 +39,9 @@ METRIC = "loop-closure frames/sec (SP+LG+MixVPR+kNN)"
 UNIT = "frames/s"
 WORKLOAD = ("full loop_fusion keyframe pipe, EuRoC-shaped synthetic stream: 480x752 gray, SuperPoint 512 kpts + "
             "SP_RE 150 pts (shared encoder) + MixVPR 320x320 + cosine kNN k=3 over 10k+ rows + LightGlue 150x662 every frame")
-# algorithmic work: conv1b = 360960 x 64 x 576 MAC per frame
-CONV1B_FLOP_PER_FRAME = 2.0 * 360960 * 64 * 576
+# algorithmic work of the dominant kernel, which computes conv1a (360960 x 64 x 9 MAC) AND conv1b
+# (360960 x 64 x 576 MAC) per frame in one launch (conv_halo.cu, FUSE == 2)
+CONV1B_FLOP_PER_FRAME = 2.0 * 360960 * 64 * (576 + 9)
 FRAME_GFLOP = 61.22 + 16.21 + 23.98          # SP + MixVPR + LightGlue(150x662), SURVEY §8(d)
 
 
@@ -188,7 +190,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="frames per rank per round")
+    ap.add_argument("--batch", type=int, default=64, help="frames per rank per round")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -348,17 +350,25 @@ def main():
     tf_peak, hbm_peak, peak_src = _peaks()
     k_ms = probe_ms / max(probe_n, 1)
     achieved = CONV1B_FLOP_PER_FRAME * b / (k_ms * 1e-3) / 1e12 if probe_n else None
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 8 frames/launch from the committed
-    # ncu --set full capture (profiles/r01_conv1b_halo_ncu_raw_selected.txt): 369.8 MB + 79.6 MB
-    traffic = (369.773056e6 + 79.608576e6) * b / 8.0
-    roofline = {"kernel": "conv3x3_halo64_kernel (conv1b 3x3 64->64 + ReLU + 2x2 max-pool, halo-tile implicit GEMM, %d frames/launch)" % b,
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 32 frames/launch from the committed
+    # ncu --set full capture (profiles/r01_conv1a1b_fused_ncu_raw_selected.txt): 11.7 MB (the u8 frames) + 315.8 MB
+    # (the pooled fp16 output; algorithmic bytes are 11.6 + 369.6 MB, part of the output was still in L2 at kernel end)
+    traffic = (11.669504e6 + 315.845376e6) * b / 32.0
+    roofline = {"kernel": "conv3x3_halo64_kernel<2> (SuperPoint conv1a 1->64 on the tensor cores inside conv1b 3x3 64->64 + ReLU + 2x2 max-pool, halo-tile implicit GEMM, %d frames/launch)" % b,
                 "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                 "frac": (achieved / tf_peak) if achieved else None, "traffic": traffic,
-                "traffic_source": "ncu --set full, profiles/r01_conv1b_halo_ncu_raw_selected.txt (scaled by batch/8)",
+                "traffic_source": "ncu --set full, profiles/r01_conv1a1b_fused_ncu_raw_selected.txt (scaled by batch/32)",
                 "peak_source": peak_src,
                 "avg_launch_ms": k_ms, "launches_timed": probe_n,
                 "flop_per_launch": CONV1B_FLOP_PER_FRAME * b,
                 "whole_frame_tflops": FRAME_GFLOP * value / 1e3}
+    # the north-star's bar is stated on the dominant STAGE (SuperPoint's convolutions, 61.22 GFLOP/frame = 56 % of the
+    # frame's flops): all of its kernels together, from the per-stage event pass
+    sp_ms = stage_ms.get("sp_convs", 0.0) / 3.0
+    if sp_ms > 0:
+        sp_tf = 61.22e9 * b / (sp_ms * 1e-3) / 1e12
+        roofline["dominant_stage"] = {"name": "SuperPoint conv stage (conv1a..convDb, %d frames)" % b, "ms": sp_ms,
+                                      "achieved": sp_tf, "unit": "TFLOP/s", "frac": sp_tf / tf_peak}
     cpu = None
     if not args.no_cpu_baseline:
         from oracle import weights
