@@ -296,6 +296,16 @@ class Engine:
                                         int(relu), int(pool), int(out_blocked), _ptr(y, C.c_float)))
         return y
 
+    def dbg_conv3x3_halo128(self, x_nhwc, w_oihw, bias, relu=True, pool=False, out_blocked=True):
+        x, w, bp = _f32(x_nhwc), _f32(w_oihw), _f32(bias)
+        n, h, wd, cin = x.shape
+        cout = w.shape[0]
+        ho, wo = (h // 2, wd // 2) if pool else (h, wd)
+        y = np.zeros((n, ho, wo, cout), np.float32)
+        _chk(_lib.dv_dbg_conv3x3_halo128(self._h, _ptr(x, C.c_float), _ptr(w, C.c_float), _ptr(bp, C.c_float), n, h, wd,
+                                         cin, cout, int(relu), int(pool), int(out_blocked), _ptr(y, C.c_float)))
+        return y
+
     def dbg_nms_select(self, score_map):
         s = _f32(score_map); h8, w8 = s.shape
         nms = np.zeros_like(s); k = self.cfg.max_kpts

@@ -395,6 +395,60 @@ dv_status dv_dbg_conv3x3_halo64(dv_engine* h, const float* x, const float* wgt, 
   return DV_OK;
 }
 
+dv_status dv_dbg_conv3x3_halo128(dv_engine* h, const float* x, const float* wgt, const float* bias, int32_t n, int32_t hh,
+                                 int32_t ww, int32_t cin, int32_t cout, int32_t relu, int32_t pool, int32_t out_blocked,
+                                 float* y) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  if (!x || !wgt || !bias || !y || n <= 0 || hh <= 0 || ww <= 0) { set_error("dv_dbg_conv3x3_halo128: bad argument"); return DV_ERR_INVALID; }
+  const size_t nx = (size_t)n * hh * ww * cin;
+  const int ho = pool ? hh / 2 : hh, wo = pool ? ww / 2 : ww;
+  const size_t ny = (size_t)n * ho * wo * cout;
+  std::vector<float> xb(nx), wr((size_t)cout * 9 * cin), yb(ny);
+  for (int b = 0; b < n; ++b)
+    for (int yy = 0; yy < hh; ++yy)
+      for (int xx = 0; xx < ww; ++xx)
+        for (int c = 0; c < cin; ++c)
+          xb[((((size_t)b * (cin / 8) + c / 8) * hh + yy) * ww + xx) * 8 + c % 8] = x[(((size_t)b * hh + yy) * ww + xx) * cin + c];
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * cin + c] = wgt[((size_t)o * cin + c) * 9 + t];
+  float *dx32 = nullptr, *dw32 = nullptr, *dy32 = nullptr, *dbias = nullptr;
+  __half *dx = nullptr, *dw = nullptr, *dy = nullptr;
+  DV_CUDA_OK(cudaMalloc(&dx32, nx * 4)); DV_CUDA_OK(cudaMalloc(&dx, nx * 2));
+  DV_CUDA_OK(cudaMalloc(&dw32, wr.size() * 4)); DV_CUDA_OK(cudaMalloc(&dw, wr.size() * 2));
+  DV_CUDA_OK(cudaMalloc(&dy, ny * 2 + 64)); DV_CUDA_OK(cudaMalloc(&dy32, ny * 4));
+  DV_CUDA_OK(cudaMalloc(&dbias, (size_t)cout * 4));
+  DV_CUDA_OK(cudaMemsetAsync(dy, 0, ny * 2, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dx32, xb.data(), nx * 4, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dw32, wr.data(), wr.size() * 4, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)cout * 4, cudaMemcpyHostToDevice, e->st));
+  f32_to_f16(dx32, dx, (int64_t)nx, e->st);
+  f32_to_f16(dw32, dw, (int64_t)wr.size(), e->st);
+  Halo128Plan pl;
+  int rc = plan_conv3x3_halo128(&pl, dx, n, hh, ww, cin, dw, cout, dbias, dy, out_blocked, relu, pool);
+  if (!rc) rc = launch_conv_halo128(pl, n, e->st);
+  if (!rc) {
+    f16_to_f32(dy, dy32, (int64_t)ny, e->st);
+    cudaError_t ce = cudaMemcpyAsync(yb.data(), dy32, ny * 4, cudaMemcpyDeviceToHost, e->st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
+    if (ce != cudaSuccess) { set_error(std::string("dv_dbg_conv3x3_halo128: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
+  }
+  cudaFree(dx32); cudaFree(dx); cudaFree(dw32); cudaFree(dw); cudaFree(dy); cudaFree(dy32); cudaFree(dbias);
+  if (rc) return (dv_status)rc;
+  if (out_blocked) {
+    for (int b = 0; b < n; ++b)
+      for (int yy = 0; yy < ho; ++yy)
+        for (int xx = 0; xx < wo; ++xx)
+          for (int c = 0; c < cout; ++c)
+            y[(((size_t)b * ho + yy) * wo + xx) * cout + c] =
+                yb[((((size_t)b * (cout / 8) + c / 8) * ho + yy) * wo + xx) * 8 + c % 8];
+  } else {
+    memcpy(y, yb.data(), ny * 4);
+  }
+  return DV_OK;
+}
+
 dv_status dv_dbg_read(dv_engine* h, const char* name, float* dst, int64_t capacity, int64_t* count) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);

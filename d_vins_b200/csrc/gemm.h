@@ -105,6 +105,22 @@ int plan_conv3x3_halo64(HaloPlan* pl, const __half* x_blocked, int n_cap, int H,
 int launch_conv_halo64(const HaloPlan& pl, int n_img, cudaStream_t st);
 int conv_halo_init();
 
+// ---- halo-tile 3x3 convolution for 64/128 -> 128k channels (conv_halo128.cu): 32x8-pixel tiles (two M=128 row blocks),
+// activations fetched once per tile, weights streamed through a ring of [128 x 64] blocks.  Input channel-blocked.
+struct Halo128Plan {
+  CUtensorMap tmX, tmW;
+  int H = 0, W = 0, n_cap = 0, tiles_w = 0, tiles_h = 0, cin = 0, cout = 0;
+  const float* bias = nullptr;
+  __half* out = nullptr;
+  int out_blocked = 1;     // 1: [N][cout/8][Ho][Wo][8]; 0: NHWC [N][Ho][Wo][cout]
+  int relu = 1, pool = 0;
+};
+int plan_conv3x3_halo128(Halo128Plan* pl, const __half* x_blocked, int n_cap, int H, int W, int cin,
+                         const __half* w /*[cout, 9*cin]*/, int cout, const float* bias, __half* out, int out_blocked,
+                         int relu, int pool);
+int launch_conv_halo128(const Halo128Plan& pl, int n_img, cudaStream_t st);
+int conv_halo128_init();
+
 // ---- fused LightGlue FFN block (lg_ffn.cu) ---------------------------------------------------------------------------
 struct FfnPlan {
   CUtensorMap tmX, tmW0, tmW3;

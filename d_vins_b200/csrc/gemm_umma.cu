@@ -260,6 +260,8 @@ int gemm_init() {
   if (rc) return rc;
   rc = gemm_wres_init();
   if (rc) return rc;
+  rc = conv_halo128_init();
+  if (rc) return rc;
   return conv_halo_init();
 }
 

@@ -24,6 +24,8 @@ struct SpNet {
   float *logits = nullptr, *dmap = nullptr;             // [B*h8*w8, 80], [B*h8*w8, 256]
   GemmPlan p1b, p2a, p2b, p3a, p3b, p4a, p4b, pPD, pPb, pDb;
   HaloPlan h1b, h2a, h2b;                               // weights-stationary halo kernels for the 64->64 layers
+  Halo128Plan h3a, h3b, h4a, h4b, hPD;                  // 256-pixel halo tiles, streamed weights (conv_halo128.cu)
+  bool use_halo128 = false;
   bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
   int fuse1a_tc = 0;                                    // DV_SP_FUSE1A=2: conv1a on the tensor cores inside conv1b (conv_halo.cu FUSE == 2)
   bool fuse1a = false;                                  // DV_SP_FUSE1A=1: conv1a inside conv1b's producer (correct, but the
@@ -550,7 +552,18 @@ int sp_init(Engine* e) {
     if (s->fuse1a) { s->h1b.gray = s->gray; s->h1b.w1a = s->w1a; s->h1b.b1a = s->b1a; }   // conv1a inside conv1b's producer
   }
   DV_TRY(plan_conv3x3_halo64(&s->h2a, s->a1b, B, H2, W2, s->w[1], s->bias[1], s->a2a, 1, 1, 0));
-  DV_TRY(plan_conv3x3_halo64(&s->h2b, s->a2a, B, H2, W2, s->w[2], s->bias[2], s->a2b, 0, 1, 1));
+  {
+    const char* env = getenv("DV_SP_HALO128");           // 0: tap-per-TMA implicit GEMM for the 128-channel layers (A/B)
+    s->use_halo128 = s->use_halo && !(env && env[0] == '0');
+  }
+  // conv2b+pool -> (blocked when the 128-channel layers run on the halo kernel, else NHWC)
+  DV_TRY(plan_conv3x3_halo64(&s->h2b, s->a2a, B, H2, W2, s->w[2], s->bias[2], s->a2b, s->use_halo128 ? 1 : 0, 1, 1));
+  // conv3a -> conv3b+pool -> conv4a -> conv4b stay channel-blocked; convPa ++ convDa writes NHWC for the 1x1 heads
+  DV_TRY(plan_conv3x3_halo128(&s->h3a, s->a2b, B, H4, W4, 64, s->w[3], 128, s->bias[3], s->a3a, 1, 1, 0));
+  DV_TRY(plan_conv3x3_halo128(&s->h3b, s->a3a, B, H4, W4, 128, s->w[4], 128, s->bias[4], s->a3b, 1, 1, 1));
+  DV_TRY(plan_conv3x3_halo128(&s->h4a, s->a3b, B, h8, w8, 128, s->w[5], 128, s->bias[5], s->a4a, 1, 1, 0));
+  DV_TRY(plan_conv3x3_halo128(&s->h4b, s->a4a, B, h8, w8, 128, s->w[6], 128, s->bias[6], s->a4b, 1, 1, 0));
+  DV_TRY(plan_conv3x3_halo128(&s->hPD, s->a4b, B, h8, w8, 128, s->w[7], 512, s->bias[7], s->aPD, 0, 1, 0));
   DV_TRY(plan_conv3x3(&s->p1b, s->a1a, B, H, W, 64, s->w[0], 64, ep16(s->a1b, 64, s->bias[0], 1, 1)));
   DV_TRY(plan_conv3x3(&s->p2a, s->a1b, B, H2, W2, 64, s->w[1], 64, ep16(s->a2a, 64, s->bias[1], 1, 0)));
   DV_TRY(plan_conv3x3(&s->p2b, s->a2a, B, H2, W2, 64, s->w[2], 64, ep16(s->a2b, 64, s->bias[2], 1, 1)));
@@ -572,11 +585,14 @@ int sp_init(Engine* e) {
   e->dbg[s->use_halo ? "conv1a_blocked" : "conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
   e->dbg[s->use_halo ? "conv1b_pool_blocked" : "conv1b_pool"] = {s->a1b, (int64_t)H2 * W2 * 64, 1};
   e->dbg[s->use_halo ? "conv2a_blocked" : "conv2a"] = {s->a2a, (int64_t)H2 * W2 * 64, 1};
-  e->dbg["conv2b_pool"] = {s->a2b, (int64_t)H4 * W4 * 64, 1};
-  e->dbg["conv3a"] = {s->a3a, (int64_t)H4 * W4 * 128, 1};
-  e->dbg["conv3b_pool"] = {s->a3b, (int64_t)h8 * w8 * 128, 1};
-  e->dbg["conv4a"] = {s->a4a, (int64_t)h8 * w8 * 128, 1};
-  e->dbg["conv4b"] = {s->a4b, (int64_t)h8 * w8 * 128, 1};
+  {
+    const char* sfx = s->use_halo128 ? "_blocked" : "";   // [C/8][H][W][8] on the halo path, NHWC otherwise
+    e->dbg[std::string("conv2b_pool") + sfx] = {s->a2b, (int64_t)H4 * W4 * 64, 1};
+    e->dbg[std::string("conv3a") + sfx] = {s->a3a, (int64_t)H4 * W4 * 128, 1};
+    e->dbg[std::string("conv3b_pool") + sfx] = {s->a3b, (int64_t)h8 * w8 * 128, 1};
+    e->dbg[std::string("conv4a") + sfx] = {s->a4a, (int64_t)h8 * w8 * 128, 1};
+    e->dbg[std::string("conv4b") + sfx] = {s->a4b, (int64_t)h8 * w8 * 128, 1};
+  }
   e->dbg["convPD"] = {s->aPD, (int64_t)h8 * w8 * 512, 1};
   e->dbg["logits"] = {s->logits, (int64_t)h8 * w8 * 80, 0};
   e->dbg["dmap"] = {s->dmap, (int64_t)h8 * w8 * 256, 0};
@@ -627,11 +643,19 @@ int sp_run_encoder(Engine* e, int b) {
     DV_TRY(launch_gemm(s->p2a, b, e->st));
     DV_TRY(launch_gemm(s->p2b, b, e->st));
   }
-  DV_TRY(launch_gemm(s->p3a, b, e->st));
-  DV_TRY(launch_gemm(s->p3b, b, e->st));
-  DV_TRY(launch_gemm(s->p4a, b, e->st));
-  DV_TRY(launch_gemm(s->p4b, b, e->st));
-  DV_TRY(launch_gemm(s->pPD, b, e->st));
+  if (s->use_halo128) {
+    DV_TRY(launch_conv_halo128(s->h3a, b, e->st));
+    DV_TRY(launch_conv_halo128(s->h3b, b, e->st));
+    DV_TRY(launch_conv_halo128(s->h4a, b, e->st));
+    DV_TRY(launch_conv_halo128(s->h4b, b, e->st));
+    DV_TRY(launch_conv_halo128(s->hPD, b, e->st));
+  } else {
+    DV_TRY(launch_gemm(s->p3a, b, e->st));
+    DV_TRY(launch_gemm(s->p3b, b, e->st));
+    DV_TRY(launch_gemm(s->p4a, b, e->st));
+    DV_TRY(launch_gemm(s->p4b, b, e->st));
+    DV_TRY(launch_gemm(s->pPD, b, e->st));
+  }
   const int rows = b * e->h8 * e->w8;
   DV_TRY(launch_gemm(s->pPb, rows, e->st));
   DV_TRY(launch_gemm(s->pDb, rows, e->st));

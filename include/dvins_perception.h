@@ -177,6 +177,11 @@ dv_status dv_dbg_conv3x3(dv_engine* e, const float* x, const float* wgt, const f
  * the entry point converts to / from the channel-blocked device layout.  out_blocked selects the device output layout. */
 dv_status dv_dbg_conv3x3_halo64(dv_engine* e, const float* x, const float* wgt, const float* bias, int32_t n, int32_t h,
                                 int32_t w, int32_t relu, int32_t pool, int32_t out_blocked, float* y);
+/* Same op through the 256-pixel halo-tile kernel for cin in {64, 128}, cout a multiple of 128 (conv_halo128.cu: the
+ * SuperPoint conv3a..convPa/Da layers, deep_net.cpp:527-688 / export/superpoint.py:159-173). */
+dv_status dv_dbg_conv3x3_halo128(dv_engine* e, const float* x, const float* wgt, const float* bias, int32_t n, int32_t h,
+                                 int32_t w, int32_t cin, int32_t cout, int32_t relu, int32_t pool, int32_t out_blocked,
+                                 float* y);
 /* NMS + border + threshold + top-k on a caller-supplied f32 score map [h8,w8] (integer stage in isolation). */
 dv_status dv_dbg_nms_select(dv_engine* e, const float* score_map, int32_t h8, int32_t w8, float* nms_out,
                             int32_t* kpts_xy, float* scores, int32_t* n);

@@ -72,6 +72,30 @@ def test_conv3x3_halo64(eng, n, h, w, pool, blocked):
     assert err < 4e-3, err
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,pool,blocked", [
+    (1, 32, 8, 128, 128, False, True), (1, 32, 8, 64, 128, False, False), (2, 40, 24, 128, 128, True, True),
+    (1, 37, 29, 128, 128, True, False), (1, 37, 29, 64, 128, False, True), (2, 60, 94, 128, 512, False, False),
+    (3, 120, 188, 128, 128, True, True), (2, 47, 155, 128, 256, False, True)])
+def test_conv3x3_halo128(eng, n, h, w, cin, cout, pool, blocked):
+    """256-pixel halo-tile kernel (conv_halo128.cu): halo fetched once per 32x8 tile, weights streamed, two M=128 row
+    blocks per weight block; ragged tiles, odd sizes (pool floors), several 128-column output chunks."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(h * w + n + cin + cout)
+    x = rng.standard_normal((n, h, w, cin)).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, 3, 3)) * np.sqrt(2.0 / (9 * cin))).astype(np.float32)
+    bias = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+    y = eng.dbg_conv3x3_halo128(x, wt, bias, relu=True, pool=pool, out_blocked=blocked)
+    xt = torch.from_numpy(_q(x)).permute(0, 3, 1, 2).double()
+    r = F.relu(F.conv2d(xt, torch.from_numpy(_q(wt)).double(), torch.from_numpy(bias).double(), padding=1))
+    if pool:
+        r = F.max_pool2d(r, 2, 2)
+    ref = r.permute(0, 2, 3, 1).numpy()
+    assert y.shape == ref.shape
+    err = np.abs(y - ref).max()
+    assert err < 4e-3, err
+
+
 @pytest.mark.parametrize("M,N,K", [(1000, 256, 512), (300, 512, 256), (77, 768, 256), (5000, 192, 64),
                                    (129, 136, 128), (4099, 1024, 320),
                                    # weights-resident kernel (gemm_wres.cu): 256-column slabs (K <= 256), 128-column
