@@ -23,6 +23,9 @@ struct EpiParams {
   const float* rope_cs = nullptr;
   const float* rope_sn = nullptr;
   int rope_cols = 0;
+  // the same tables as one fp16 array [rows, 64] = (cos_j, sin_j) interleaved: 128 contiguous bytes per row instead of
+  // two 128-byte fp32 rows (weights-resident kernel: the per-thread row fetch was its L1 bottleneck, profiles/README.md)
+  const __half* rope16 = nullptr;
   // out16 in the channel-blocked layout [rows / blocked_hw][N/8][blocked_hw][8] (input format of conv_halo.cu);
   // persistent kernel only, plain (non-conv) mode.  0 = row-major.
   int blocked_hw = 0;

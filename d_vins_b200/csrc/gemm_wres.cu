@@ -145,16 +145,18 @@ __global__ void __launch_bounds__(320, 1)
       const bool active = row0 < p.M;                    // warp-uniform
       const bool writer = row0 + lane < p.M;
       // rotary tables of this row (32 cos + 32 sin), shared by every head of the slab; fetched before the wait
-      const bool rope_tile = ep.rope_cs && col_base < ep.rope_cols && active;
-      float4 cs4[8], sn4[8];
+      const bool rope_tile = ep.rope16 && col_base < ep.rope_cols && active;
+      // (cos_j, sin_j) of this row's 32 rotary angles as 64 fp16 values: 8 x 16-byte loads of one 128-byte line
+      uint4 rt[8];
       if (rope_tile && writer) {
-        const float4* cp = reinterpret_cast<const float4*>(ep.rope_cs + (long)(row0 + lane) * 32);
-        const float4* sp = reinterpret_cast<const float4*>(ep.rope_sn + (long)(row0 + lane) * 32);
+        const uint4* rp = reinterpret_cast<const uint4*>(ep.rope16 + (long)(row0 + lane) * 64);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { cs4[g] = __ldg(cp + g); sn4[g] = __ldg(sp + g); }
+        for (int g = 0; g < 8; ++g) rt[g] = __ldg(rp + g);
       } else {
+        const __half2 id = __floats2half2_rn(1.f, 0.f);
+        const uint32_t idu = *reinterpret_cast<const uint32_t*>(&id);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { cs4[g] = make_float4(1.f, 1.f, 1.f, 1.f); sn4[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        for (int g = 0; g < 8; ++g) rt[g] = make_uint4(idu, idu, idu, idu);
       }
       for (int sub = 0; sub < n_sub; ++sub) {
         const int lcol = sub * 128 + h * 64;             // first column of this warp inside the slab
@@ -225,14 +227,15 @@ __global__ void __launch_bounds__(320, 1)
             if (rope) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                const float4 c4 = cs4[ci * 4 + g], s4 = sn4[ci * 4 + g];
-                const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+                const uint4 t4 = rt[ci * 4 + g];                    // angles ci * 16 + g * 4 + {0..3}
+                const uint32_t tw[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
                 for (int x = 0; x < 4; ++x) {
+                  const float2 csn = __half22float2(*reinterpret_cast<const __half2*>(&tw[x]));   // (cos, sin)
                   const int jj = g * 4 + x;
                   const float x0 = v[2 * jj], x1 = v[2 * jj + 1];
-                  v[2 * jj] = x0 * cc[x] - x1 * ss[x];
-                  v[2 * jj + 1] = x1 * cc[x] + x0 * ss[x];
+                  v[2 * jj] = x0 * csn.x - x1 * csn.y;
+                  v[2 * jj + 1] = x1 * csn.x + x0 * csn.y;
                 }
               }
             }
@@ -308,7 +311,7 @@ static bool wres_config(const GemmPlan& pl, long m_tiles, WresCfg* c) {
   const EpiParams& ep = p.epi;
   if (!g_use_wres || !pl.staged) return false;              // same operand / alignment rules as the staged kernel
   if ((p.K & 63) || p.K > 512 || (p.N & 127)) return false;
-  if (ep.rope_cs && (ep.rope_cols & 127)) return false;
+  if (ep.rope_cs && (!ep.rope16 || (ep.rope_cols & 127))) return false;
   if (m_tiles < 8) return false;
   const bool f32 = ep.out32 || ep.res32, f16 = ep.out16 || ep.res16;
   const uint32_t staging = (f32 ? 65536u : 0u) + (f16 ? 32768u : 0u);

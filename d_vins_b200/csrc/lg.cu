@@ -52,6 +52,7 @@ struct LgNet {
   __half* ffh = nullptr;               // [T,512] FFN pre-LayerNorm activations (fp16)
   __half* ffg = nullptr;               // [T,512]
   float *cs = nullptr, *sn = nullptr;  // [T,32] rotary cos / sin
+  __half* rope16 = nullptr;            // [T,64] the same as fp16 (cos_j, sin_j) pairs (weights-resident GEMM epilogue)
   __half* md = nullptr;                // [T,256]
   float* z = nullptr;                  // [T] matchability logits
   float* sim = nullptr;                // [P, segcap, segcap]
@@ -77,7 +78,7 @@ struct LgNet {
 // normalisation: deep_net.cpp:839-841,:874-880 ((kp - [W/2,H/2]) / max(W/2,H/2), integer halves).
 __global__ void k_lg_load(const LgSeg* __restrict__ segs, const float* __restrict__ Wr, float* __restrict__ x32,
                           __half* __restrict__ X2, float* __restrict__ cs, float* __restrict__ sn,
-                          float* __restrict__ kpts_out) {
+                          __half* __restrict__ rope16, float* __restrict__ kpts_out) {
   const LgSeg sg = segs[blockIdx.y];
   const int rows = lg_pad(sg.n);
   const int warps = blockDim.x >> 5, lane = threadIdx.x & 31;
@@ -106,8 +107,10 @@ __global__ void k_lg_load(const LgSeg* __restrict__ segs, const float* __restric
     const float sc = fmaxf(sw, sh);
     const float nx = __fdiv_rn(kx - sw, sc), ny = __fdiv_rn(ky - sh, sc);
     const float pr = nx * Wr[lane * 2] + ny * Wr[lane * 2 + 1];
-    cs[t * 32 + lane] = cosf(pr);
-    sn[t * 32 + lane] = sinf(pr);
+    const float cv = cosf(pr), sv = sinf(pr);
+    cs[t * 32 + lane] = cv;
+    sn[t * 32 + lane] = sv;
+    *reinterpret_cast<__half2*>(rope16 + t * 64 + lane * 2) = __floats2half2_rn(cv, sv);
   }
 }
 
@@ -147,6 +150,11 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 
 #define ATT_LD 72   // padded smem row (halves): 144 B stride -> conflict-free ldmatrix
+__device__ __forceinline__ float ex2_ftz(float x) {      // bare MUFU.EX2 (exp2f adds denormal range handling around it)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 #define ATT_WARPS 4                 // warps per CTA: 16 query rows each (8 = 128-row tiles measured slower: coarser waves)
 #define ATT_QT (ATT_WARPS * 16)
@@ -229,27 +237,32 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* 
         mma16816(s[np * 2 + 1], qa[ks], b2, b3);
       }
     }
-    // mask keys >= nk, online softmax (rows r0 = lane/4 and r0+8)
+    // mask keys >= nk (only the last chunk can be partial: block-uniform branch), online softmax (rows r0 = lane/4, r0+8)
     float mx[2] = {-INFINITY, -INFINITY};
+    if (k0 + 64 > jb.nk) {
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      const int key = k0 + nt * 8 + (lane & 3) * 2;
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = k0 + nt * 8 + (lane & 3) * 2;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (key + (j & 1) >= jb.nk) s[nt][j] = -INFINITY;
-        mx[j >> 1] = fmaxf(mx[j >> 1], s[nt][j]);
+        for (int j = 0; j < 4; ++j)
+          if (key + (j & 1) >= jb.nk) s[nt][j] = -INFINITY;
       }
     }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mx[j >> 1] = fmaxf(mx[j >> 1], s[nt][j]);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
       mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
     }
-    float corr[2], mnew[2];
+    float corr[2], mnew[2], nms[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mnew[h] = fmaxf(mrow[h], mx[h]);            // finite: every chunk holds >= 1 valid key
-      corr[h] = exp2f((mrow[h] - mnew[h]) * sl2);
+      corr[h] = ex2_ftz((mrow[h] - mnew[h]) * sl2);
+      nms[h] = -mnew[h] * sl2;                    // exp2(s * sl2 - m * sl2): one FFMA + MUFU per score
       mrow[h] = mnew[h];
       lrow[h] *= corr[h];
     }
@@ -258,15 +271,18 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* 
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float p = exp2f((s[nt][j] - mnew[j >> 1]) * sl2);
+        const float p = ex2_ftz(fmaf(s[nt][j], sl2, nms[j >> 1]));
         s[nt][j] = p;
         ps[j >> 1] += p;
       }
     lrow[0] += ps[0];
     lrow[1] += ps[1];
+    // the running maxima settle after the first chunks: skip the 32 rescale multiplies when no row of the warp moved
+    if (__any_sync(0xffffffffu, corr[0] != 1.f || corr[1] != 1.f)) {
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      o[dt][0] *= corr[0]; o[dt][1] *= corr[0]; o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
+      for (int dt = 0; dt < 8; ++dt) {
+        o[dt][0] *= corr[0]; o[dt][1] *= corr[0]; o[dt][2] *= corr[1]; o[dt][3] *= corr[1];
+      }
     }
     // O += P V
 #pragma unroll
@@ -581,6 +597,7 @@ int lg_init(Engine* e) {
   DV_TRY(e->alloc(&g->ffg, (size_t)T * 512));
   DV_TRY(e->alloc(&g->cs, (size_t)T * 32));
   DV_TRY(e->alloc(&g->sn, (size_t)T * 32));
+  DV_TRY(e->alloc(&g->rope16, (size_t)T * 64));
   DV_TRY(e->alloc(&g->md, (size_t)T * 256));
   DV_TRY(e->alloc(&g->z, (size_t)T));
   DV_TRY(e->alloc(&g->kpts, (size_t)T * 2));
@@ -662,7 +679,7 @@ int lg_init(Engine* e) {
     DV_TRY(e->upload_f16(w->data, &L.cf3)); DV_TRY(e->upload_f32(b->data, &L.bcf3));
     // plans (A operands are fixed buffers; rows are set at launch)
     { EpiParams ep = ep16(g->qkv, 768, L.bqkv);
-      if (gemm_is_persistent()) { ep.rope_cs = g->cs; ep.rope_sn = g->sn; ep.rope_cols = 512; }   // rotary fused into the store
+      if (gemm_is_persistent()) { ep.rope_cs = g->cs; ep.rope_sn = g->sn; ep.rope16 = g->rope16; ep.rope_cols = 512; }   // rotary fused into the store
       DV_TRY(plan_gemm(&L.p_qkv, g->X2, 512, T, L.wqkv, 256, 768, 256, ep)); }
     DV_TRY(plan_gemm(&L.p_out, g->ctx, 256, T, L.wout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bout)));
     DV_TRY(plan_gemm(&L.p_f0, g->X2, 512, T, L.wf0, 512, 512, 512, ep16(g->ffh, 512, L.bf0)));
@@ -764,7 +781,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
   DV_CUDA_OK(cudaMemcpyAsync(g->jobs_cross, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(g->ju_self, g->h_ju, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(g->ju_cross, g->h_ju + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
-  k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->kpts);
+  k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
   DV_LAUNCHED(e, 1);
   const dim3 agrid(cdiv(max_n_any, ATT_QT), LG_HEADS, 2 * P);
   for (int i = 0; i < LG_LAYERS; ++i) {
