@@ -124,6 +124,19 @@ int plan_conv3x3_halo128(Halo128Plan* pl, const __half* x_blocked, int n_cap, in
 int launch_conv_halo128(const Halo128Plan& pl, int n_img, cudaStream_t st);
 int conv_halo128_init();
 
+// ---- ResNet stem 7x7/2 3->64 as one implicit GEMM with in-kernel im2col (stem_conv.cu) ---------------------------------
+struct StemPlan {
+  CUtensorMap tmW;
+  const __half* img = nullptr;   // [N,320,320,3] fp16
+  const float* bias = nullptr;
+  __half* out = nullptr;         // [N,160,160,64] fp16
+  int n_cap = 0;
+};
+int plan_stem_conv(StemPlan* pl, const __half* img16, int n_cap, const __half* w /*[64,192], k=(r*7+s)*3+c*/, const float* bias,
+                   __half* out);
+int launch_stem_conv(const StemPlan& pl, int n_img, cudaStream_t st);
+int stem_conv_init();
+
 // ---- fused LightGlue FFN block (lg_ffn.cu) ---------------------------------------------------------------------------
 struct FfnPlan {
   CUtensorMap tmX, tmW0, tmW3;

@@ -262,6 +262,8 @@ int gemm_init() {
   if (rc) return rc;
   rc = conv_halo128_init();
   if (rc) return rc;
+  rc = stem_conv_init();
+  if (rc) return rc;
   return conv_halo_init();
 }
 

@@ -37,6 +37,7 @@ struct LgLayer {
 
 struct LgNet {
   int P = 1, segcap = 1024, Tcap = 0;
+  int ln_grid = 148 * 8;               // grid-stride LayerNorm+GELU kernel: 8 CTAs of 8 warps per SM
   bool fused_ffn = false;              // DV_LG_FUSED_FFN=1: single-kernel FFN (lg_ffn.cu; correct, but weight re-streaming
                                        // per 128-row block makes it no faster than the 3-kernel path yet - r01 notes)
   float* Wr = nullptr;                 // [32,2]
@@ -338,44 +339,72 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 // LayerNorm(512, eps 1e-5, affine) + exact (erf) GELU, fp32 in -> fp16 out.  One warp per token.
-__global__ void k_lg_ln_gelu(const __half* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
-                             __half* __restrict__ out, int64_t T) {
+// Grid-stride over tokens, TWO tokens per warp per iteration with 128-bit loads (4 x 16 B in flight per lane: the
+// one-token / 8-byte version sat at 2.5 TB/s of L2-resident traffic, latency-bound); gamma / beta of the lane's 16
+// columns stay in registers.  Lane l owns columns [8l, 8l+8) and [256 + 8l, 256 + 8l + 8).
+__global__ void __launch_bounds__(256) k_lg_ln_gelu(const __half* __restrict__ x, const float* __restrict__ g,
+                                                    const float* __restrict__ b, __half* __restrict__ out, int64_t T) {
   pdl_trigger();
-  pdl_wait();
-  const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (t >= T) return;
-  const uint2* xr = reinterpret_cast<const uint2*>(x + t * 512);
-  float v[16];
+  float gg[16], bb[16];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint2 a = xr[c * 32 + lane];
-    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
-    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
-    v[c * 4] = lo.x; v[c * 4 + 1] = lo.y; v[c * 4 + 2] = hi.x; v[c * 4 + 3] = hi.y;
-  }
-  float s = 0.f;
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s += v[i];
+    for (int q = 0; q < 2; ++q) {
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + h * 256 + lane * 8 + q * 4));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + h * 256 + lane * 8 + q * 4));
+      gg[h * 8 + q * 4] = g4.x; gg[h * 8 + q * 4 + 1] = g4.y; gg[h * 8 + q * 4 + 2] = g4.z; gg[h * 8 + q * 4 + 3] = g4.w;
+      bb[h * 8 + q * 4] = b4.x; bb[h * 8 + q * 4 + 1] = b4.y; bb[h * 8 + q * 4 + 2] = b4.z; bb[h * 8 + q * 4 + 3] = b4.w;
+    }
+  pdl_wait();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t t0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2; t0 < T; t0 += warps * 2) {
+    uint4 raw[2][2];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.f / 512.f);
-  float q = 0.f;
+    for (int k = 0; k < 2; ++k) {
+      const bool ok = t0 + k < T;
+      const uint4* xr = reinterpret_cast<const uint4*>(x + (t0 + (ok ? k : 0)) * 512);
+      raw[k][0] = xr[lane];
+      raw[k][1] = xr[32 + lane];
+    }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q += d * d; }
+    for (int k = 0; k < 2; ++k) {
+      if (t0 + k >= T) break;                          // warp-uniform
+      float v[16];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.f / sqrtf(q * (1.f / 512.f) + 1e-5f);
+      for (int h = 0; h < 2; ++h) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&raw[k][h]);
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int col = (c * 32 + lane) * 4;
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + col)), bb = __ldg(reinterpret_cast<const float4*>(b + col));
-    float y[4] = {(v[c * 4] - mean) * rstd * gg.x + bb.x, (v[c * 4 + 1] - mean) * rstd * gg.y + bb.y,
-                  (v[c * 4 + 2] - mean) * rstd * gg.z + bb.z, (v[c * 4 + 3] - mean) * rstd * gg.w + bb.w};
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = __half22float2(h2[q]);
+          v[h * 8 + 2 * q] = f.x; v[h * 8 + 2 * q + 1] = f.y;
+        }
+      }
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) y[j] = gelu_erf(y[j]);
-    __align__(8) __half2 h[2] = {__floats2half2_rn(y[0], y[1]), __floats2half2_rn(y[2], y[3])};
-    *reinterpret_cast<uint2*>(out + t * 512 + col) = *reinterpret_cast<uint2*>(h);
+      for (int i = 0; i < 16; ++i) s += v[i];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / 512.f);
+      float q2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q2 += d * d; }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+      const float rstd = 1.f / sqrtf(q2 * (1.f / 512.f) + 1e-5f);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __align__(16) __half2 hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = h * 8 + 2 * q;
+          const float y0 = gelu_erf((v[i] - mean) * rstd * gg[i] + bb[i]);
+          const float y1 = gelu_erf((v[i + 1] - mean) * rstd * gg[i + 1] + bb[i + 1]);
+          hv[q] = __floats2half2_rn(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(out + (t0 + k) * 512 + h * 256 + lane * 8) = *reinterpret_cast<const uint4*>(hv);
+      }
+    }
   }
 }
 
@@ -797,7 +826,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
       DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
     } else {
       DV_TRY(launch_gemm(L.p_f0, T, e->st));
-      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(cdiv(T, 8)), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
+      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
                             (const float*)L.ln_b, g->ffg, (int64_t)T));
       DV_TRY(launch_gemm(L.p_f3, T, e->st));
     }
@@ -810,7 +839,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
       DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
     } else {
       DV_TRY(launch_gemm(L.pc_f0, T, e->st));
-      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(cdiv(T, 8)), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
+      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
                             (const float*)L.cln_b, g->ffg, (int64_t)T));
       DV_TRY(launch_gemm(L.pc_f3, T, e->st));
     }

@@ -28,6 +28,8 @@ struct MixNet {
   float* y32 = nullptr;         // [B*400, 256]
   float* gdesc = nullptr;       // [B, 512]
   std::vector<GemmPlan> plans;
+  StemPlan stem;                       // 7x7/2 stem as one implicit GEMM with in-kernel im2col (stem_conv.cu)
+  bool fused_stem = true;              // DV_MIX_STEM=0: im2col kernel + GEMM (A/B)
   std::vector<HaloPlan> hplans;        // layer1's 64->64 3x3 convs run on the weights-stationary halo kernel
   std::vector<std::function<int(Engine*, int)>> ops;
   int n_launch = 0;
@@ -205,24 +207,46 @@ __global__ void k_transpose_f2h(const float* __restrict__ in, __half* __restrict
   }
 }
 
-// LayerNorm over rows of length D (eps 1e-5, affine), fp32 in -> fp16 out.  One warp per row.
-__global__ void k_layernorm_f2h(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ bta,
-                                __half* __restrict__ out, int64_t rows, int D) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// LayerNorm over rows of length D <= 512, D % 4 == 0 (eps 1e-5, affine), fp32 in -> fp16 out.  One warp per row, the row
+// held in registers (one pass over memory, 128-bit loads; the three-pass scalar version ran at 2.4 TB/s of L2 traffic).
+__global__ void __launch_bounds__(256) k_layernorm_f2h(const float* __restrict__ x, const float* __restrict__ g,
+                                                       const float* __restrict__ bta, __half* __restrict__ out,
+                                                       int64_t rows, int D) {
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* xr = x + row * D;
-  float s = 0.f;
-  for (int i = lane; i < D; i += 32) s += xr[i];
+  const int nv = D >> 2;                                  // float4 per row
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[4];
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)D;
-  float v = 0.f;
-  for (int i = lane; i < D; i += 32) { const float d = xr[i] - mean; v += d * d; }
+    for (int k = 0; k < 4; ++k) v[k] = (lane + 32 * k < nv) ? xr[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float s = 0.f;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  const float rstd = 1.f / sqrtf(v / (float)D + 1e-5f);
-  for (int i = lane; i < D; i += 32) out[row * D + i] = __float2half_rn((xr[i] - mean) * rstd * g[i] + bta[i]);
+    for (int k = 0; k < 4; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < nv) {
+        const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.f / sqrtf(q / (float)D + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < nv) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + lane + 32 * k);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bta) + lane + 32 * k);
+        __align__(8) __half2 h[2] = {
+            __floats2half2_rn((v[k].x - mean) * rstd * gg.x + bb.x, (v[k].y - mean) * rstd * gg.y + bb.y),
+            __floats2half2_rn((v[k].z - mean) * rstd * gg.z + bb.z, (v[k].w - mean) * rstd * gg.w + bb.w)};
+        *reinterpret_cast<uint2*>(out + row * D + (lane + 32 * k) * 4) = *reinterpret_cast<const uint2*>(h);
+      }
+  }
 }
 
 // row_proj (400 -> 2) on y [B,400,256], flatten index c*2 + r, L2-normalise -> [B,512].  One block per frame:
@@ -371,17 +395,24 @@ int mix_init(Engine* e) {
     const int total = b * 320 * 320;
     k_mix_pre<<<cdiv(total, 256), 256, 0, en->st>>>(en->d_img, en->H, en->W, en->img_ch, mm->d2i[0], mm->d2i[1],
                                                    mm->d2i[2], mm->d2i[3], mm->d2i[4], mm->d2i[5], mm->img16, total);
+    if (mm->fused_stem) return launch_stem_conv(mm->stem, b, en->st);
     k_im2col_stem<<<dim3(160 / STEM_OXB, 160, b), 256, 0, en->st>>>(mm->img16, mm->col);
     return (int)DV_OK;
   });
   m->n_launch += 2;
   {
+    const char* env = getenv("DV_MIX_STEM");
+    m->fused_stem = !(env && env[0] == '0');
     Folded f;
     DV_TRY(fold_bn(e, pre + "conv1", pre + "bn1", 64, 147, &f));
     std::vector<float> wp = repack_khwc(f.w, 64, 3, 7, 7, 192);
     __half* dw; float* db;
     DV_TRY(add_w(wp, f.b, &dw, &db));
-    DV_TRY(add_gemm(m->col, 192, (int)P160, dw, 192, 64, 192, epi16(m->xa, 64, db, 1), 25600));
+    if (m->fused_stem) {
+      DV_TRY(plan_stem_conv(&m->stem, m->img16, B, dw, db, m->xa));
+    } else {
+      DV_TRY(add_gemm(m->col, 192, (int)P160, dw, 192, 64, 192, epi16(m->xa, 64, db, 1), 25600));
+    }
   }
   m->ops.push_back([](Engine* en, int b) {
     MixNet* mm = en->mix;
@@ -492,7 +523,8 @@ int mix_init(Engine* e) {
     m->ops.push_back([i](Engine* en, int b) {
       MixNet* mm = en->mix;
       const int64_t rows = (int64_t)b * 1024;
-      k_layernorm_f2h<<<(unsigned)cdiv64(rows, 8), 256, 0, en->st>>>(mm->x32, mm->ln_g[i], mm->ln_b[i], mm->ln16, rows, 400);
+      k_layernorm_f2h<<<(unsigned)std::min<int64_t>(cdiv64(rows, 8), 148 * 8), 256, 0, en->st>>>(mm->x32, mm->ln_g[i], mm->ln_b[i],
+                                                                                            mm->ln16, rows, 400);
       return (int)DV_OK;
     });
     m->n_launch++;
