@@ -159,10 +159,16 @@ __device__ __forceinline__ float ex2_ftz(float x) {      // bare MUFU.EX2 (exp2f
 
 #define ATT_WARPS 4                 // warps per CTA: 16 query rows each (8 = 128-row tiles measured slower: coarser waves)
 #define ATT_QT (ATT_WARPS * 16)
+#define ATT_STAGES 3
+#define ATT_SMEM (2 * ATT_STAGES * 64 * ATT_LD * 2)   // bytes
 __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* __restrict__ jobs, float scale) {
-  __shared__ __align__(16) __half sKb[2][64 * ATT_LD];   // double-buffered K / V chunks (cp.async)
-  __shared__ __align__(16) __half sVb[2][64 * ATT_LD];
-  __half* sQ = &sKb[0][0];     // the 128-row Q tile is staged through the K buffers once, then lives in registers
+  // three-stage K / V ring (cp.async, prefetch distance 2): ONE block barrier per 64-key chunk.  55 KB dynamic smem,
+  // four CTAs per SM.  The Q tile is staged through K stage 2 (first written after the first barrier) and then lives
+  // in registers, so its load overlaps the first two K / V prefetches.
+  extern __shared__ __align__(16) __half att_smem[];
+  __half (*sKb)[64 * ATT_LD] = reinterpret_cast<__half (*)[64 * ATT_LD]>(att_smem);
+  __half (*sVb)[64 * ATT_LD] = reinterpret_cast<__half (*)[64 * ATT_LD]>(att_smem + ATT_STAGES * 64 * ATT_LD);
+  __half* sQ = &sKb[ATT_STAGES - 1][0];
   pdl_trigger();
   pdl_wait();
   const AttnJob jb = jobs[blockIdx.z];
@@ -173,20 +179,6 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* 
   const __half* Q = jb.q + head * 64;
   const __half* K = jb.k + head * 64;
   const __half* V = jb.v + head * 64;
-  // Q tile -> smem (rows beyond nq read as zero)
-  for (int i = tid; i < ATT_QT * 8; i += ATT_WARPS * 32) {
-    const int r = i >> 3, c = (i & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q0 + r < jb.nq) v = __ldg(reinterpret_cast<const uint4*>(Q + (int64_t)(q0 + r) * jb.ldq + c));
-    *reinterpret_cast<uint4*>(&sQ[r * ATT_LD + c]) = v;
-  }
-  __syncthreads();
-  uint32_t qa[4][4];   // A fragments of this warp's 16 query rows, 4 k-steps over d
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks)
-    ldsm_x4(qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3],
-            &sQ[(warp * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8]);
-  __syncthreads();     // every warp holds its Q fragments: the buffers may now receive K / V
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -210,18 +202,29 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* 
   };
   const int n_it = (jb.nk + 63) >> 6;
   load_kv(0, 0);
+  if (n_it > 1) load_kv(1, 64);
+  // Q tile -> smem (rows beyond nq read as zero)
+  for (int i = tid; i < ATT_QT * 8; i += ATT_WARPS * 32) {
+    const int r = i >> 3, c = (i & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q0 + r < jb.nq) v = __ldg(reinterpret_cast<const uint4*>(Q + (int64_t)(q0 + r) * jb.ldq + c));
+    *reinterpret_cast<uint4*>(&sQ[r * ATT_LD + c]) = v;
+  }
+  __syncthreads();
+  uint32_t qa[4][4];   // A fragments of this warp's 16 query rows, 4 k-steps over d
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+    ldsm_x4(qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3],
+            &sQ[(warp * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8]);
   for (int it = 0; it < n_it; ++it) {
     const int k0 = it * 64;
-    if (it + 1 < n_it) {
-      load_kv((it + 1) & 1, k0 + 64);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();
-    const __half* sK = sKb[it & 1];
-    const __half* sV = sVb[it & 1];
-    if (q0 + warp * 16 >= jb.nq) { __syncthreads(); continue; }   // warp-uniform: this warp's 16 rows are all padding
+    if (it + 1 < n_it) asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk `it` landed (it+1 may be in flight)
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // chunk `it` visible to all warps; every warp is past chunk it-1 (and past its Q ldmatrix)
+    if (it + 2 < n_it) load_kv((it + 2) % ATT_STAGES, k0 + 128);               // overwrites the stage of chunk it-1
+    const __half* sK = sKb[it % ATT_STAGES];
+    const __half* sV = sVb[it % ATT_STAGES];
+    if (q0 + warp * 16 >= jb.nq) continue;                        // warp-uniform: this warp's 16 rows are all padding
     // S = Q K^T : 16 x 64 per warp
     float s[8][4];
 #pragma unroll
@@ -301,7 +304,6 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* 
         mma16816(o[dp * 2 + 1], pa, b2, b3);
       }
     }
-    __syncthreads();   // everyone is done with this stage before the next prefetch overwrites it
   }
   // finalise: row sums across the quad, normalise, store fp16
 #pragma unroll
@@ -611,6 +613,7 @@ int lg_init(Engine* e) {
   g->segcap = (e->cfg.lg_max_kpts + 127) & ~127;
   g->Tcap = g->P * 2 * g->segcap;
   { const char* env = getenv("DV_LG_FUSED_FFN"); g->fused_ffn = (env && env[0] == '1'); }
+  DV_CUDA_OK(cudaFuncSetAttribute(k_lg_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   DV_TRY(lg_ffn_init());
   const int T = g->Tcap, P = g->P, SC = g->segcap;
   {
@@ -820,7 +823,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     if (!gemm_is_persistent())
       k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
     if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_self, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), 0, e->st, (const AttnJob*)g->jobs_self, 0.125f));
+    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_self, 0.125f));
     DV_TRY(launch_gemm(L.p_out, T, e->st));
     if (g->fused_ffn) {
       DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
@@ -833,7 +836,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
     // cross block
     DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
     if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_cross, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), 0, e->st, (const AttnJob*)g->jobs_cross, 0.125f));
+    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_cross, 0.125f));
     DV_TRY(launch_gemm(L.pc_out, T, e->st));
     if (g->fused_ffn) {
       DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
