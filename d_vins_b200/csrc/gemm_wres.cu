@@ -30,6 +30,8 @@ namespace dv {
 
 struct WresCfg {
   int m_tiles, slab, n_slabs, group, stages;
+  int epi_warps;     // 8: warp (q, h) drains column half h of every 128-column sub-tile; 4: warp q drains both halves in
+                     // turn through one set of staging boxes (fp32 + fp16 outputs with a 128 KB slab: 48 KB of staging)
   uint32_t a_off, sb32_off, sb16_off, bar_off, bias_off, smem_bytes;
 };
 
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(320, 1)
     if (ep.res32) prefetch_tmap(&tmR32);
     if (ep.res16) prefetch_tmap(&tmR16);
     for (int s = 0; s < c.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], (uint32_t)c.epi_warps); }
     for (int e = 0; e < 8; ++e) mbar_init(&rbar[e], 1);
     mbar_init(w_bar, 1);
     fence_barrier_init();
@@ -124,18 +126,19 @@ __global__ void __launch_bounds__(320, 1)
         tc_commit(&acc_full[a]);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue: 8 warps
+  } else if (warp - 2 < c.epi_warps) {
+    // ------------------------------------------------------------------ epilogue: 8 (or 4) warps
     const int e = warp - 2;
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int h = e >> 2;                      // column half of each 128-column sub-tile
+    const int nh = c.epi_warps == 8 ? 1 : 2;   // column halves this warp walks per 128-column sub-tile
+    const int h0 = c.epi_warps == 8 ? (e >> 2) : 0;
     uint8_t* b32 = smem + c.sb32_off + e * 8192;
     uint8_t* b16 = smem + c.sb16_off + e * 4096;
     uint64_t* rb = &rbar[e];
     const uint32_t rowoff = (uint32_t)lane * 128u;
     const uint32_t swz = (uint32_t)(lane & 7) << 4;
     const bool has_res = (F32 && ep.res32) || (F16 && ep.res16);
-    const int n_sub = c.slab >> 7;
+    const int n_sub = (c.slab >> 7) * nh;      // drain units per tile: (sub-tile, half) pairs of this warp
     uint32_t rphase = 0;
     int it = 0;
     long long t_rd = 0, t_acc = 0, t_work = 0, t_all0 = p.dbg ? clock64() : 0;     // DV_GEMM_DBG cycle counters
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(320, 1)
         for (int g = 0; g < 8; ++g) rt[g] = make_uint4(idu, idu, idu, idu);
       }
       for (int sub = 0; sub < n_sub; ++sub) {
-        const int lcol = sub * 128 + h * 64;             // first column of this warp inside the slab
+        const int lcol = (sub / nh) * 128 + (h0 + sub % nh) * 64;   // first column of this unit inside the slab
         const int colw = col_base + lcol;                // ... and in the output matrix
         // (1) the previous TMA stores must have finished READING the staging boxes
         long long t0 = p.dbg ? clock64() : 0;
@@ -314,12 +317,15 @@ static bool wres_config(const GemmPlan& pl, long m_tiles, WresCfg* c) {
   if (ep.rope_cs && (!ep.rope16 || (ep.rope_cols & 127))) return false;
   if (m_tiles < 8) return false;
   const bool f32 = ep.out32 || ep.res32, f16 = ep.out16 || ep.res16;
-  const uint32_t staging = (f32 ? 65536u : 0u) + (f16 ? 32768u : 0u);
   const uint32_t fixed = 1024u /*alignment slack*/ + 512u /*barriers*/ + 1024u /*bias*/;
-  for (int slab = 256; slab >= 128; slab >>= 1) {
+  for (int cand = 0; cand < 4; ++cand) {                    // (slab 256, 8 warps), (256, 4), (128, 8), (128, 4)
+    const int slab = cand < 2 ? 256 : 128, epi = (cand & 1) ? 4 : 8;
+    const uint32_t st32 = f32 ? 8192u * (uint32_t)epi : 0u, st16 = f16 ? 4096u * (uint32_t)epi : 0u;
+    const uint32_t staging = st32 + st16;
     if (p.N % slab) continue;
     const uint32_t wbytes = (uint32_t)slab * (uint32_t)p.K * 2u;
     if (wbytes + staging + fixed + 3u * 16384u > WRES_SMEM_MAX) continue;
+    c->epi_warps = epi;
     int stages = (int)((WRES_SMEM_MAX - wbytes - staging - fixed) / 16384u);
     if (stages > 8) stages = 8;
     c->slab = slab;
@@ -331,8 +337,8 @@ static bool wres_config(const GemmPlan& pl, long m_tiles, WresCfg* c) {
     c->m_tiles = (int)m_tiles;
     c->a_off = wbytes;
     c->sb32_off = c->a_off + (uint32_t)stages * 16384u;
-    c->sb16_off = c->sb32_off + (f32 ? 65536u : 0u);
-    c->bar_off = c->sb16_off + (f16 ? 32768u : 0u);
+    c->sb16_off = c->sb32_off + st32;
+    c->bar_off = c->sb16_off + st16;
     c->bias_off = c->bar_off + 512u;
     c->smem_bytes = c->bias_off + 1024u + 1024u;
     return true;

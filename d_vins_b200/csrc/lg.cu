@@ -329,12 +329,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_lg_attention(const AttnJob* 
 // rounding of the result.  ~16 instructions (2 MUFU) instead of ~30; the kernel is issue-bound (ncu: sm 62 %).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));        // bare MUFU (1 ulp): __frcp_rn /
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));     // exp2f expand to ~10 more each
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float erfc_z = poly * t * exp2f(-1.4426950408889634f * z * z);   // 1 - erf(z), z >= 0
+  const float erfc_z = poly * t * e;                                                   // 1 - erf(z), z >= 0
   const float half_x = 0.5f * x;
   // x >= 0: 0.5 x (2 - erfc);  x < 0: 0.5 x erfc
   return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
@@ -393,15 +395,17 @@ __global__ void __launch_bounds__(256) k_lg_ln_gelu(const __half* __restrict__ x
       for (int i = 0; i < 16; ++i) { const float d = v[i] - mean; q2 += d * d; }
 #pragma unroll
       for (int o = 16; o; o >>= 1) q2 += __shfl_xor_sync(0xffffffffu, q2, o);
-      const float rstd = 1.f / sqrtf(q2 * (1.f / 512.f) + 1e-5f);
+      const float rstd = rsqrtf(q2 * (1.f / 512.f) + 1e-5f);
+      const float nmr = -mean * rstd;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         __align__(16) __half2 hv[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = h * 8 + 2 * q;
-          const float y0 = gelu_erf((v[i] - mean) * rstd * gg[i] + bb[i]);
-          const float y1 = gelu_erf((v[i + 1] - mean) * rstd * gg[i + 1] + bb[i + 1]);
+          // ((v - mean) * rstd) * g + b as two FMAs: n = v * rstd - mean * rstd
+          const float y0 = gelu_erf(fmaf(fmaf(v[i], rstd, nmr), gg[i], bb[i]));
+          const float y1 = gelu_erf(fmaf(fmaf(v[i + 1], rstd, nmr), gg[i + 1], bb[i + 1]));
           hv[q] = __floats2half2_rn(y0, y1);
         }
         *reinterpret_cast<uint4*>(out + (t0 + k) * 512 + h * 256 + lane * 8) = *reinterpret_cast<const uint4*>(hv);
