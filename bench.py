@@ -220,7 +220,7 @@ def main():
         dist.barrier()
         wpath = make_weights()
     eng = capi.Engine(device=local, height=H, width=W, max_batch=b, max_vio=160, weights_path=wpath,
-                      bank_capacity=BANK_PREFILL + (args.steps * 2 + args.warmup * 2 + 8) * b * world + 64,
+                      bank_capacity=BANK_PREFILL + (args.steps * 3 + max(args.warmup, 3) * 2 + 12) * b * world + 64,
                       store_capacity=2 * b * world + b, world_size=world, rank=rank)
     if world > 1:
         uid = [capi.comm_unique_id() if rank == 0 else None]
@@ -247,13 +247,22 @@ def main():
     h2d = [0]
     d2h = [0]
 
+    prefetched = [False]
+
     def one_round(upload: bool):
+        """upload=True: the round's frames come from pinned host memory.  Uploads are asynchronous and double-buffered
+        in the engine, so round R+1's frames are queued right after round R's extraction and travel while round R is
+        being searched and matched; every round still costs exactly one upload inside the timed region."""
         R = round_no[0]
         ids = np.arange(b, dtype=np.int64) + (R * world + rank) * b        # contiguous block per rank per round
-        if upload:
+        if upload and not prefetched[0]:
             eng.batch_upload_ptr(b, pool[R % npool].data_ptr(), H * W, W)
             h2d[0] += b * H * W
         eng.batch_extract(vio, nv, ids)
+        if upload:
+            eng.batch_upload_ptr(b, pool[(R + 1) % npool].data_ptr(), H * W, W)   # next round's frames
+            h2d[0] += b * H * W
+            prefetched[0] = True
         h2d[0] += vio.nbytes + nv.nbytes
         d2h[0] += 4 * b
         eng.batch_commit(b)
@@ -313,9 +322,17 @@ def main():
         one_round(upload=True)
     ms_e2e = eng.timer_stop()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     ms_e2e = max_over_ranks(ms_e2e)
     h2d_step, d2h_step = h2d[0] // args.steps, d2h[0] // args.steps
+    # ---------------- (3) the device-resident loop once more: separates the cost of the uploads from clock / power
+    # drift between the two timed regions (the e2e loop runs on a GPU that has been at full load for longer)
+    barrier()
+    eng.timer_start()
+    for _ in range(args.steps):
+        one_round(upload=False)
+    ms_dev2 = max_over_ranks(eng.timer_stop())
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
 
     # ---------------- per-stage shares (separate pass; event records perturb the timed loops)
     eng.stats_enable(True)
@@ -384,9 +401,12 @@ def main():
         "config": {"workload": WORKLOAD, "frames_per_rank_per_step": b, "global_frames_per_step": b * world,
                    "parallelism": "frame-sharded x%d, one NCCL all-gather of [b,512] per round" % world,
                    "l2": "per-step working set (>= %.1f GB of activations) far exceeds the 126 MB L2; no explicit flush" % (0.16 * b),
-                   "weights": "seeded synthetic (oracle/weights.py)"},
+                   "weights": "seeded synthetic (oracle/weights.py)",
+                   "e2e_input": "pinned host frames, asynchronous double-buffered upload queued one round ahead (one "
+                                "upload per round inside the timed region)"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "device_resident_rerun_after": frames_total / (ms_dev2 / 1000.0)},
         "gpu_launches": int(launches),
         "p50_match_ms": p50,
         "stage_ms_per_round": {k: v / 3.0 for k, v in stage_ms.items()},

@@ -9,6 +9,7 @@ using namespace dv;
 
 namespace dv {
 int ensure_encoder(Engine* e) {
+  e->adopt_upload();
   if (e->cur_b <= 0) { set_error("no frame uploaded"); return DV_ERR_INVALID; }
   if (!e->enc_done) { DV_TRY(sp_run_encoder(e, e->cur_b)); e->enc_done = true; }
   return DV_OK;
@@ -32,12 +33,15 @@ dv_status dv_frame_upload(dv_engine* h, const uint8_t* img, int32_t height, int3
     set_error("dv_frame_upload: frame size differs from the configured network size");
     return DV_ERR_UNSUPPORTED;
   }
-  StageScope sc(e, ST_COPY);
   const size_t row = (size_t)width * channels;
+  DV_CUDA_OK(cudaEventSynchronize(e->ev_img_ready));      // the previous upload has left the pinned staging buffer
   for (int y = 0; y < height; ++y) memcpy(e->h_img + (size_t)y * row, img + (size_t)y * stride, row);
-  DV_CUDA_OK(cudaMemcpyAsync(e->d_img, e->h_img, row * height, cudaMemcpyHostToDevice, e->st));
+  uint8_t* dst = e->image_begin_upload();
+  DV_CUDA_OK(cudaMemcpyAsync(dst, e->h_img, row * height, cudaMemcpyHostToDevice, e->st_copy));
+  e->image_end_upload();
   e->img_ch = channels;
   e->cur_b = 1;
+  e->next_pending = false;
   e->enc_done = e->det_done = e->mix_done = false;
   return DV_OK;
 }

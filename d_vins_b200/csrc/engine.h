@@ -43,10 +43,43 @@ struct Engine {
   std::vector<void*> pinned;
 
   // raw frames of the current batch
-  uint8_t* d_img = nullptr;    // [B, H, W, ch] u8 as uploaded
+  // Frames are double-buffered and uploaded on their own stream: dv_batch_upload / dv_frame_upload return as soon as
+  // the copy is queued, so the upload of keyframe round R+1 overlaps the matching of round R.  `d_img` is the buffer
+  // of the most recent upload; consumers call image_acquire() first and image_release() after their last read.
+  uint8_t* d_img = nullptr;    // [B, H, W, ch] u8 as uploaded (= d_img_buf[img_idx])
+  uint8_t* d_img_buf[2] = {nullptr, nullptr};
+  int img_idx = 0;
+  bool img_pending = false;    // an upload has been queued that the compute stream has not waited for yet
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_img_ready = nullptr, ev_img_free[2] = {nullptr, nullptr};
   uint8_t* h_img = nullptr;    // pinned staging
+  // upload side: pick the other buffer, make the copy stream wait until the compute stream has released it
+  uint8_t* image_begin_upload() {
+    const int nb = img_idx ^ 1;
+    cudaStreamWaitEvent(st_copy, ev_img_free[nb], 0);
+    return d_img_buf[nb];
+  }
+  void image_end_upload() {
+    cudaEventRecord(ev_img_ready, st_copy);
+    img_idx ^= 1;
+    d_img = d_img_buf[img_idx];
+    img_pending = true;
+  }
+  // compute side
+  void image_acquire() {
+    if (img_pending) { cudaStreamWaitEvent(st, ev_img_ready, 0); img_pending = false; }
+  }
+  void image_release() { cudaEventRecord(ev_img_free[img_idx], st); }
   int img_ch = 1;
-  int cur_b = 0;               // frames in the current batch
+  int cur_b = 0;               // frames in the current (being / last extracted) batch
+  // dv_batch_upload may run one round ahead: the uploaded batch becomes current only when something consumes it
+  // (dv_batch_extract, or the lazily evaluated per-frame entry points), so commit / search / match of the previous
+  // round stay valid while its successor's frames are already travelling.
+  int next_b = 0;
+  bool next_pending = false;
+  void adopt_upload() {
+    if (next_pending) { cur_b = next_b; enc_done = det_done = mix_done = false; next_pending = false; }
+  }
   bool enc_done = false, det_done = false, mix_done = false;
 
   SpNet* sp = nullptr;

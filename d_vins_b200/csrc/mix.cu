@@ -573,7 +573,9 @@ int mix_run(Engine* e, int b) {
   MixNet* m = e->mix;
   if (!m) { set_error("MixVPR not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   StageScope sc(e, ST_MIX);
+  e->image_acquire();
   for (auto& op : m->ops) DV_TRY(op(e, b));
+  e->image_release();       // k_mix_pre (first op) was the last reader queued for this buffer
   DV_CUDA_OK(cudaGetLastError());
   DV_LAUNCHED(e, m->n_launch);
   return DV_OK;
@@ -589,6 +591,7 @@ extern "C" dv_status dv_mix_describe(dv_engine* h, float* des512) {
   if (!h) { dv::set_error("null engine"); return DV_ERR_INVALID; }
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!des512) { set_error("dv_mix_describe: null output"); return DV_ERR_INVALID; }
+  e->adopt_upload();
   if (e->cur_b <= 0) { set_error("no frame uploaded"); return DV_ERR_INVALID; }
   if (!e->mix_done) { DV_TRY(mix_run(e, e->cur_b)); e->mix_done = true; }
   DV_CUDA_OK(cudaMemcpyAsync(des512, e->mix->gdesc, 512 * sizeof(float), cudaMemcpyDeviceToHost, e->st));

@@ -610,6 +610,7 @@ int sp_run_encoder(Engine* e, int b) {
   SpNet* s = e->sp;
   if (!s) { set_error("SuperPoint not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   StageScope sc(e, ST_SP_CONV);
+  e->image_acquire();
   const int H = e->H, W = e->W;
   const int64_t npix = (int64_t)b * H * W;
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
@@ -643,6 +644,7 @@ int sp_run_encoder(Engine* e, int b) {
     DV_TRY(launch_gemm(s->p2a, b, e->st));
     DV_TRY(launch_gemm(s->p2b, b, e->st));
   }
+  e->image_release();     // k_gray / the fused conv1a+conv1b kernel were the encoder's only readers of the u8 frames
   if (s->use_halo128) {
     DV_TRY(launch_conv_halo128(s->h3a, b, e->st));
     DV_TRY(launch_conv_halo128(s->h3b, b, e->st));

@@ -169,19 +169,22 @@ dv_status dv_batch_upload(dv_engine* h, int32_t b, const uint8_t* imgs, int64_t 
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!imgs || b < 1 || b > e->B || stride < e->W || frame_stride < (int64_t)stride * e->H) { set_error("dv_batch_upload: bad arguments"); return DV_ERR_INVALID; }
-  StageScope sc(e, ST_COPY);
   const size_t fb = (size_t)e->H * e->W;
+  // asynchronous on the copy stream into the buffer the compute stream is not using: the caller may queue round R+1's
+  // frames while round R is still matching (the source must stay valid until the next dv_batch_extract / dv_sync)
+  uint8_t* dst = e->image_begin_upload();
   if (stride == e->W && frame_stride == (int64_t)fb) {
     // contiguous (typically already pinned by the caller): one async copy straight from the caller's buffer
-    DV_CUDA_OK(cudaMemcpyAsync(e->d_img, imgs, fb * b, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(dst, imgs, fb * b, cudaMemcpyHostToDevice, e->st_copy));
   } else {
-    DV_CUDA_OK(cudaMemcpy2DAsync(e->d_img, e->W, imgs, stride, e->W, (size_t)e->H, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpy2DAsync(dst, e->W, imgs, stride, e->W, (size_t)e->H, cudaMemcpyHostToDevice, e->st_copy));
     for (int i = 1; i < b; ++i)
-      DV_CUDA_OK(cudaMemcpy2DAsync(e->d_img + fb * i, e->W, imgs + frame_stride * i, stride, e->W, (size_t)e->H, cudaMemcpyHostToDevice, e->st));
+      DV_CUDA_OK(cudaMemcpy2DAsync(dst + fb * i, e->W, imgs + frame_stride * i, stride, e->W, (size_t)e->H, cudaMemcpyHostToDevice, e->st_copy));
   }
+  e->image_end_upload();
   e->img_ch = 1;
-  e->cur_b = b;
-  e->enc_done = e->det_done = e->mix_done = false;
+  e->next_b = b;
+  e->next_pending = true;
   return DV_OK;
 }
 
@@ -190,6 +193,7 @@ dv_status dv_batch_extract(dv_engine* h, int32_t b, const float* vio_xy, const i
   Engine* e = reinterpret_cast<Engine*>(h);
   Store* s = e->store;
   if (!e->sp || !e->mix) { set_error("dv_batch_extract: engine created without weights"); return DV_ERR_INVALID; }
+  e->adopt_upload();
   if (b < 1 || b != e->cur_b || !vio_xy || !n_vio || !frame_ids) { set_error("dv_batch_extract: b must equal the uploaded batch"); return DV_ERR_INVALID; }
   const int V = e->cfg.max_vio, K = e->cfg.max_kpts;
   for (int i = 0; i < b; ++i) {

@@ -74,3 +74,36 @@ def test_batch_match_uses_store(eng):
     _, _, nsp0 = eng.store_read(0)
     ok = np.mean(m[:, 1] == nsp0 + m[:, 0])
     assert ok >= 0.5, ok
+
+
+def test_upload_runs_one_round_ahead(eng):
+    """dv_batch_upload is asynchronous and double-buffered: round R+1's frames may be queued right after round R's
+    extraction; commit / search / match of round R keep working on R, and R+1's extraction sees R+1's frames."""
+    from oracle import knn, synth
+    st = synth.Stream(480, 752, period=12, margin=64)
+    b = 4
+    fa = np.stack([st.frame(t) for t in range(20, 20 + b)])
+    fb = np.stack([st.frame(t) for t in range(30, 30 + b)])
+    vio = np.zeros((b, 160, 2), np.float32); nv = np.full((b,), 30, np.int32)
+    for i in range(b):
+        vio[i, :30] = synth.vio_points(30, 480, 752, 90 + i)
+    ids_a, ids_b = np.arange(100, 100 + b, dtype=np.int64), np.arange(104, 104 + b, dtype=np.int64)
+    eng.bank_import(np.zeros((0, 512), np.float32))
+    # reference: strictly sequential
+    eng.batch_upload(fa); eng.batch_extract(vio, nv, ids_a)
+    ga = [eng.batch_read_global(i) for i in range(b)]
+    eng.batch_upload(fb); eng.batch_extract(vio, nv, ids_b)
+    gb = [eng.batch_read_global(i) for i in range(b)]
+    assert not np.array_equal(ga[0], gb[0])
+    # pipelined: B uploaded while A is still the current round
+    eng.bank_import(np.zeros((0, 512), np.float32))
+    eng.batch_upload(fa); eng.batch_extract(vio, nv, ids_a)
+    eng.batch_upload(fb)                                            # prefetch
+    assert all(np.array_equal(eng.batch_read_global(i), ga[i]) for i in range(b))
+    assert eng.batch_commit(b) == 0
+    D, I = eng.batch_search([knn.nb_limit(int(t)) for t in range(b)])
+    assert np.array_equal(I[:, 0], np.arange(b))                    # every frame retrieves itself (nb = t + 1)
+    res = eng.batch_match(ids_a, ids_a)
+    assert len(res) == b
+    eng.batch_extract(vio, nv, ids_b)                               # consumes the prefetched frames
+    assert all(np.array_equal(eng.batch_read_global(i), gb[i]) for i in range(b))
