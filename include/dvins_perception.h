@@ -77,7 +77,8 @@ void dv_destroy(dv_engine* e);
  * ---------------------------------------------------------------------------------------------- */
 
 /* One H2D copy of the frame, shared by SP, SP_RE and MixVPR (the reference uploads it three times:
- * deep_net.cpp:575, :748, :1294).  img: u8, `channels` 1 (gray) or 3 (BGR), row pitch `stride` bytes. */
+ * deep_net.cpp:575, :748, :1294).  img: u8, `channels` 1 (gray) or 3 (BGR), row pitch `stride` bytes.  The frame is
+ * staged through an internal pinned buffer and copied asynchronously: `img` may be reused as soon as the call returns. */
 dv_status dv_frame_upload(dv_engine* e, const uint8_t* img, int32_t height, int32_t width, int32_t stride,
                           int32_t channels);
 
@@ -115,7 +116,10 @@ dv_status dv_lg_match(dv_engine* e, const float* kpts0, int32_t m, const float* 
  * device-resident in a per-rank feature store keyed by global keyframe index.
  * ---------------------------------------------------------------------------------------------- */
 
-/* imgs: b gray frames, frame i at imgs + i*frame_stride, row pitch `stride`. */
+/* imgs: b gray frames, frame i at imgs + i*frame_stride, row pitch `stride`.  Asynchronous and double-buffered: the copy is
+ * queued on the engine's copy stream and the call returns at once; `imgs` (ideally pinned) must stay valid until the next
+ * dv_batch_extract or dv_sync.  May be called one round ahead - after dv_batch_extract of round R, before its
+ * dv_batch_commit / dv_batch_search / dv_batch_match - so the transfer of round R+1 overlaps the matching of round R. */
 dv_status dv_batch_upload(dv_engine* e, int32_t b, const uint8_t* imgs, int64_t frame_stride, int32_t stride);
 /* SP + SP_RE + MixVPR for the b uploaded frames.  vio_xy [b, max_vio, 2] pixel coords, n_vio [b];
  * frame_ids [b] global keyframe indices.  Local features (kpts = SP ++ VIO, desc = SP ++ SP_RE, the concatenation
