@@ -214,6 +214,48 @@ class Engine:
                                 C.byref(n), C.byref(nsp)))
         return kp[:n.value], de[:n.value], nsp.value
 
+    def store_put(self, frame_id, kpts_xy, desc, n_sp):
+        k, d = _f32(kpts_xy), _f32(desc)
+        assert k.shape[0] == d.shape[0]
+        _chk(_lib.dv_store_put(self._h, C.c_int64(frame_id), _ptr(k, C.c_float), _ptr(d, C.c_float), int(k.shape[0]),
+                               int(n_sp)))
+
+    # ---------------------------------------------------------------- session persistence
+    # File "DVSESS01" (little endian): 8s magic | i64 bank_rows | i64 n_keyframes | bank f32 [rows,512] |
+    # per keyframe: i64 frame_id, i32 n_total, i32 n_sp, kpts f32 [n_total,2], desc f32 [n_total,256].
+    # Replaces the reference's per-keyframe text dumps (pose_graph.cpp:1042-1069), whose load path (:1156-1194) never
+    # restores the deep features.
+    def save_session(self, path: str, frame_ids):
+        import struct
+        bank = self.bank_export()
+        with open(path, "wb") as f:
+            f.write(b"DVSESS01")
+            f.write(struct.pack("<qq", bank.shape[0] if self.bank_size() else 0, len(frame_ids)))
+            if self.bank_size():
+                f.write(np.ascontiguousarray(bank, np.float32).tobytes())
+            for fid in frame_ids:
+                kp, de, nsp = self.store_read(int(fid))
+                f.write(struct.pack("<qii", int(fid), kp.shape[0], nsp))
+                f.write(np.ascontiguousarray(kp, np.float32).tobytes())
+                f.write(np.ascontiguousarray(de, np.float32).tobytes())
+
+    def load_session(self, path: str):
+        import struct
+        with open(path, "rb") as f:
+            if f.read(8) != b"DVSESS01":
+                raise ValueError("not a DVSESS01 file")
+            rows, nkf = struct.unpack("<qq", f.read(16))
+            bank = np.frombuffer(f.read(rows * GLOBAL_DIM * 4), np.float32).reshape(rows, GLOBAL_DIM)
+            self.bank_import(bank)
+            ids = []
+            for _ in range(nkf):
+                fid, n, nsp = struct.unpack("<qii", f.read(16))
+                kp = np.frombuffer(f.read(n * 2 * 4), np.float32).reshape(n, 2)
+                de = np.frombuffer(f.read(n * DESC_DIM * 4), np.float32).reshape(n, DESC_DIM)
+                self.store_put(fid, kp, de, nsp)
+                ids.append(fid)
+        return ids
+
     def batch_read_global(self, i):
         d = np.zeros((GLOBAL_DIM,), np.float32)
         _chk(_lib.dv_batch_read_global(self._h, i, _ptr(d, C.c_float)))

@@ -317,6 +317,26 @@ dv_status dv_store_read(dv_engine* h, int64_t frame_id, float* kpts_xy, float* d
   return DV_OK;
 }
 
+dv_status dv_store_put(dv_engine* h, int64_t frame_id, const float* kpts_xy, const float* desc, int32_t n_total,
+                       int32_t n_sp) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  Store* s = e->store;
+  if (frame_id < 0 || !kpts_xy || !desc || n_sp < 0 || n_total < n_sp || n_total > s->cap ||
+      n_sp > e->cfg.max_kpts || n_total - n_sp > e->cfg.max_vio) {
+    set_error("dv_store_put: bad arguments (n_sp <= max_kpts, n_total - n_sp <= max_vio)");
+    return DV_ERR_INVALID;
+  }
+  const int sl = (int)(frame_id % s->slots);
+  DV_CUDA_OK(cudaMemcpyAsync(s->kpts + (size_t)sl * s->cap * 2, kpts_xy, sizeof(float) * 2 * n_total, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaMemcpyAsync(s->desc + (size_t)sl * s->cap * 256, desc, sizeof(float) * 256 * n_total, cudaMemcpyHostToDevice, e->st));
+  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  s->frame_id[sl] = frame_id;
+  s->n_sp[sl] = n_sp;
+  s->n_vio[sl] = n_total - n_sp;
+  return DV_OK;
+}
+
 dv_status dv_batch_match(dv_engine* h, int32_t b, const int64_t* query_ids, const int64_t* old_ids, int32_t* matches,
                          float* mscores, int32_t* k_out) {
   DV_CHECK_ENGINE(h);

@@ -138,6 +138,12 @@ dv_status dv_batch_match(dv_engine* e, int32_t b, const int64_t* query_ids, cons
                          float* mscores, int32_t* k_out);
 /* Read one stored keyframe back (tests / persistence): kpts [n,2] f32, desc [n,256], n_sp = SuperPoint share. */
 dv_status dv_store_read(dv_engine* e, int64_t frame_id, float* kpts_xy, float* desc, int32_t* n_total, int32_t* n_sp);
+/* Restores a keyframe's local features into the store (the inverse of dv_store_read): rows [0, n_sp) are its SuperPoint
+ * keypoints / descriptors, rows [n_sp, n_total) its window points (keyframe.cpp:401-432 concatenation order).  Together
+ * with dv_bank_import this reloads a saved session - the reference's own load path (pose_graph.cpp:1156-1194) never
+ * restores the deep features it saved (:1042-1069), so a reloaded map cannot close loops there. */
+dv_status dv_store_put(dv_engine* e, int64_t frame_id, const float* kpts_xy, const float* desc, int32_t n_total,
+                       int32_t n_sp);
 /* Results of the last dv_batch_extract for frame slot i (host copies). */
 dv_status dv_batch_read_global(dv_engine* e, int32_t i, float* des512);
 

@@ -107,3 +107,40 @@ def test_upload_runs_one_round_ahead(eng):
     assert len(res) == b
     eng.batch_extract(vio, nv, ids_b)                               # consumes the prefetched frames
     assert all(np.array_equal(eng.batch_read_global(i), gb[i]) for i in range(b))
+
+
+def test_session_save_load_roundtrip(eng, weights_file, tmp_path):
+    """the descriptor bank and the keyframes' local features survive a save / load into a NEW engine
+    (dv_bank_export/import + dv_store_read/put): retrieval and a LightGlue match against a restored keyframe are
+    bit-identical to the original session's."""
+    from d_vins_b200 import capi
+    from oracle import knn, synth
+    st = synth.Stream(480, 752, period=12, margin=64)
+    b = 4
+    frames = np.stack([st.frame(t) for t in range(b)])
+    vio = np.zeros((b, 160, 2), np.float32); nv = np.full((b,), 40, np.int32)
+    for i in range(b):
+        vio[i, :40] = synth.vio_points(40, 480, 752, 70 + i)
+    ids = np.arange(b, dtype=np.int64)
+    eng.bank_import(np.zeros((0, 512), np.float32))
+    eng.batch_upload(frames); eng.batch_extract(vio, nv, ids)
+    assert eng.batch_commit(b) == 0
+    q = eng.batch_read_global(2)
+    D0, I0 = eng.bank_search(q, b)
+    m0 = eng.batch_match(np.array([3], np.int64), np.array([1], np.int64))[0]
+    path = str(tmp_path / "session.dvs")
+    eng.save_session(path, ids)
+    e2 = capi.Engine(height=480, width=752, weights_path=weights_file, max_batch=4, max_vio=160, store_capacity=16,
+                     bank_capacity=4096)
+    try:
+        assert list(e2.load_session(path)) == list(ids)
+        assert e2.bank_size() == b
+        D1, I1 = e2.bank_search(q, b)
+        assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+        for t in ids:
+            k0, d0, n0 = eng.store_read(int(t)); k1, d1, n1 = e2.store_read(int(t))
+            assert n0 == n1 and np.array_equal(k0, k1) and np.array_equal(d0, d1)
+        m1 = e2.batch_match(np.array([3], np.int64), np.array([1], np.int64))[0]
+        assert np.array_equal(m0[0], m1[0]) and np.array_equal(m0[1], m1[1])
+    finally:
+        e2.close()
