@@ -409,6 +409,10 @@ def main():
                 "device_resident_rerun_after": frames_total / (ms_dev2 / 1000.0)},
         "gpu_launches": int(launches),
         "p50_match_ms": p50,
+        # the reference only runs LightGlue when detectLoop fires; estimate for "LightGlue on 10 % of the
+        # frames" from the per-stage event pass (device-resident round time minus 90 % of its LightGlue share)
+        "lg_on_10pct_frames_estimate": (frames_total / args.steps) / max(
+            1e-9, (ms_dev / args.steps - 0.9 * stage_ms.get("lightglue", 0.0) / 3.0) / 1000.0),
         "stage_ms_per_round": {k: v / 3.0 for k, v in stage_ms.items()},
         "roofline": roofline,
         "cpu_baseline": cpu,
