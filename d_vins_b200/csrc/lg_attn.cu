@@ -30,7 +30,11 @@ constexpr int OFF_K = TILE_BYTES;              // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
 constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;  // two 128x64 tiles
 constexpr int OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+// 115 328 B: TWO CTAs per SM (2 x (115 328 + 1 KB reserved) <= 228 KB) - each CTA is one serial QK -> softmax -> PV chain,
+// the second CTA's MMAs and TMEM loads fill the first one's softmax latency.  The dynamic-smem base sits right after the
+// 1 KB reserved region, i.e. 1024-aligned; 512 B of slack cover a smaller alignment, anything worse traps.
+constexpr int ALIGN_SLACK = 512;
+constexpr int SMEM_BYTES = OFF_BAR + 128 + ALIGN_SLACK;
 }  // namespace
 
 __device__ __forceinline__ float ex2_approx(float x) {     // one MUFU op (exp2f adds range fix-ups around it)
@@ -39,7 +43,7 @@ __device__ __forceinline__ float ex2_approx(float x) {     // one MUFU op (exp2f
   return y;
 }
 
-__global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_constant__ CUtensorMap tmQKV,
+__global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                               const AttnJobU* __restrict__ jobs,
                                                               __half* __restrict__ ctx, float sl2, long long* dbg) {
   const AttnJobU jb = jobs[blockIdx.z];
@@ -48,6 +52,7 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
   const int head = blockIdx.y;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if ((int)(smem - smem_raw) > ALIGN_SLACK) __trap();
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* kv_full = q_full + 1;              // [2]
   uint64_t* kv_empty = kv_full + 2;            // [2]
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
       }
       const long long t2 = dbgt ? clock64() : 0;
       const float m_new = fmaxf(m_run, mx);                 // finite: every chunk holds >= 1 valid key
-      const float corr = exp2f((m_run - m_new) * sl2);
+      const float corr = ex2_approx((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
       float sum = 0.f;
 #pragma unroll 1
@@ -194,8 +199,10 @@ __global__ void __launch_bounds__(192, 1) lg_attn_umma_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(p_ready);
       const long long t3 = dbgt ? clock64() : 0;
+      if (__any_sync(0xffffffffu, corr != 1.f)) {          // the running maxima settle after the first chunks
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] *= corr;
+        for (int i = 0; i < 64; ++i) o[i] *= corr;
+      }
       mbar_wait(o_full, j & 1);
       const long long t4 = dbgt ? clock64() : 0;
       tc_fence_after();
