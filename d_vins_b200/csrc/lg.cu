@@ -66,8 +66,8 @@ struct LgNet {
   AttnJob *jobs_self = nullptr, *jobs_cross = nullptr, *h_jobs = nullptr;   // device x2, pinned host [4P]
   AttnJobU *ju_self = nullptr, *ju_cross = nullptr, *h_ju = nullptr;        // tcgen05 attention job tables
   CUtensorMap tm_qkv;
-  bool attn_umma = false;              // DV_LG_ATTN=umma: tcgen05 attention (lg_attn.cu; parity-green, incl. the
-                                       // MN-major V operand, but 1.8x slower than the mma.sync flash kernel so far)
+  bool attn_umma = true;               // tcgen05 attention (lg_attn.cu: MN-major V operand, O accumulated in TMEM with lazy
+                                       // rescale, two CTAs per SM); DV_LG_ATTN=mma: the mma.sync flash kernel of this file
   LgSeg *d_segs = nullptr, *h_segs = nullptr;                               // [2P]
   // staging for the host-vector API
   float *st_k = nullptr, *st_d = nullptr, *h_st_k = nullptr, *h_st_d = nullptr;   // [2*segcap,2], [2*segcap,256]
@@ -656,7 +656,8 @@ int lg_init(Engine* e) {
   DV_TRY(e->alloc(&g->ju_self, (size_t)2 * P));
   DV_TRY(e->alloc(&g->ju_cross, (size_t)2 * P));
   DV_TRY(e->alloc_pinned(&g->h_ju, (size_t)4 * P));
-  { const char* env = getenv("DV_LG_ATTN"); g->attn_umma = (env && env[0] == 'u'); }
+  // default: the tcgen05 attention (lg_attn.cu, lazy rescale, two CTAs per SM); DV_LG_ATTN=mma selects the mma.sync kernel
+  { const char* env = getenv("DV_LG_ATTN"); g->attn_umma = !(env && env[0] == 'm'); }
   DV_TRY(lg_attn_init());
   DV_TRY(plan_lg_attn(&g->tm_qkv, g->qkv, T));
   DV_TRY(e->alloc(&g->d_segs, (size_t)2 * P + (size_t)P));     // LgSeg[2P] followed by PairDesc[P] (same size class)

@@ -43,6 +43,11 @@ __device__ __forceinline__ float ex2_approx(float x) {     // one MUFU op (exp2f
   return y;
 }
 
+// LAZY = true: O accumulates in TMEM across all key chunks (the PV MMAs keep their accumulate flag) and is only rescaled -
+// read, multiplied, written back with tcgen05.st - when some row's running maximum grows by more than 2^8 over the value
+// the probabilities are scaled with (P <= 256 stays exact enough in fp16).  The softmax threads then never wait for a PV
+// product nor read O per chunk: the wait for PV(j-1) moves behind pass A of chunk j.
+template <bool LAZY>
 __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                               const AttnJobU* __restrict__ jobs,
                                                               __half* __restrict__ ctx, float sl2, long long* dbg) {
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
         for (int k = 0; k < pv_steps; ++k)                                      // up to 128 keys = 8 k-steps of 16
           // A: P tile (k >> 2), 32-byte step inside its 128-byte rows.  B: V rows [16k, 16k+16) = +2048 bytes.
           tc_mma_f16(tmem_base + 128, dp + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
-                     dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)(k != 0));
+                     dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)(LAZY ? (j | k) != 0 : k != 0));
         tc_commit(o_full);
         tc_commit(&kv_empty[s]);
       }
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cnt(p_ready);
-        mbar_wait(o_full, j & 1);
+        if (!LAZY) mbar_wait(o_full, j & 1);
         continue;
       }
       float mx = -INFINITY;
@@ -158,9 +163,33 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
         }
       }
       const long long t2 = dbgt ? clock64() : 0;
-      const float m_new = fmaxf(m_run, mx);                 // finite: every chunk holds >= 1 valid key
-      const float corr = ex2_approx((m_run - m_new) * sl2);
-      const float mb = m_new * sl2;
+      float corr = 1.f;
+      if (LAZY) {
+        // PV(j-1) has retired: the P tiles may be overwritten and O is stable for a rescale
+        if (j > 0) { mbar_wait(o_full, (j - 1) & 1); tc_fence_after(); }
+        const bool grow = j == 0 || (mx - m_run) * sl2 > 8.f;        // scale reference too small for this chunk
+        if (j == 0) {
+          m_run = mx;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          if (grow) { corr = ex2_approx((m_run - mx) * sl2); m_run = mx; l_run *= corr; }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tl + 128 + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+            tmem_st32(tl + 128 + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      } else {
+        const float m_new = fmaxf(m_run, mx);               // finite: every chunk holds >= 1 valid key
+        corr = ex2_approx((m_run - m_new) * sl2);
+        m_run = m_new;
+        l_run *= corr;
+      }
+      const float mb = m_run * sl2;
       float sum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < ngrp; ++c) {
@@ -192,19 +221,38 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
         for (int g = 0; g < 4; ++g)
           *reinterpret_cast<uint4*>(tile + (((ch0 + g) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[g];
       }
-      l_run = l_run * corr + sum;
-      m_run = m_new;
+      l_run += sum;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cnt(p_ready);
       const long long t3 = dbgt ? clock64() : 0;
-      if (__any_sync(0xffffffffu, corr != 1.f)) {          // the running maxima settle after the first chunks
+      long long t4 = t3;
+      if (!LAZY) {
+        if (__any_sync(0xffffffffu, corr != 1.f)) {          // the running maxima settle after the first chunks
 #pragma unroll
-        for (int i = 0; i < 64; ++i) o[i] *= corr;
+          for (int i = 0; i < 64; ++i) o[i] *= corr;
+        }
+        mbar_wait(o_full, j & 1);
+        t4 = dbgt ? clock64() : 0;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tl + 128 + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
+        }
+        tc_fence_before();     // order these TMEM reads before the next chunk's MMAs (released through p_ready / s_full)
       }
-      mbar_wait(o_full, j & 1);
-      const long long t4 = dbgt ? clock64() : 0;
+      if (dbgt) {
+        const long long t5 = clock64();
+        dbg[0] += t1 - t0; dbg[1] += t2 - t1; dbg[2] += t3 - t2; dbg[3] += t4 - t3; dbg[4] += t5 - t4; dbg[5] += 1;
+      }
+    }
+    if (LAZY && warp_live) {                                 // the whole sum sits in TMEM: one read at the end
+      mbar_wait(o_full, (n_chunks - 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -212,13 +260,9 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
         tmem_ld32(tl + 128 + c * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(r[i]);
       }
-      tc_fence_before();     // order these TMEM reads before the next chunk's MMAs (released through p_ready / s_full)
-      if (dbgt) {
-        const long long t5 = clock64();
-        dbg[0] += t1 - t0; dbg[1] += t2 - t1; dbg[2] += t3 - t2; dbg[3] += t4 - t3; dbg[4] += t5 - t4; dbg[5] += 1;
-      }
+      tc_fence_before();
     }
     if (q0 + row < jb.nq) {
       const float inv = 1.f / l_run;
@@ -241,7 +285,8 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
 }
 
 int lg_attn_init() {
-  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   return DV_OK;
 }
 
@@ -259,7 +304,11 @@ int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int 
   static const bool want = getenv("DV_ATTN_DBG") != nullptr;       // diagnostics: softmax-thread cycle counters
   static int calls = 0;
   if (want && !d_dbg) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
-  lg_attn_umma_kernel<<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
+  static const bool lazy = [] { const char* e = getenv("DV_ATTN_LAZY"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (lazy)
+    lg_attn_umma_kernel<true><<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
+  else
+    lg_attn_umma_kernel<false><<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
   DV_CUDA_OK(cudaGetLastError());
   if (want && ++calls == 18) {
     long long h[8];
