@@ -147,30 +147,58 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
         if (!LAZY) mbar_wait(o_full, j & 1);
         continue;
       }
-      float mx = -INFINITY;
+      // one sweep over this warp's valid 32-key groups of S: P = exp2(s * sl2 - mb) to shared memory (fp16, swizzled A
+      // operand), row sum, and the row maximum of the raw scores on the way
+      auto sweep = [&](float mb, float& sum, float& mx) {
 #pragma unroll 1
-      for (int c = 0; c < ngrp; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tl + c * 32, r);
-        tmem_ld_wait();
-        if (kbase + c * 32 + 32 <= jb.nk) {
+        for (int c = 0; c < ngrp; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tl + c * 32, r);
+          tmem_ld_wait();
+          __align__(16) __half2 hv[16];
+          if (kbase + c * 32 + 32 <= jb.nk) {                 // full 32-key group (warp-uniform): no masking
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
+            for (int i = 0; i < 16; ++i) {
+              const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
+              mx = fmaxf(mx, fmaxf(s0, s1));
+              const float p0 = ex2_approx(fmaf(s0, sl2, -mb));
+              const float p1 = ex2_approx(fmaf(s1, sl2, -mb));
+              hv[i] = __floats2half2_rn(p0, p1);
+              sum += p0 + p1;
+            }
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 16; ++i) {
+              const int key = kbase + c * 32 + 2 * i;
+              const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
+              if (key < jb.nk) mx = fmaxf(mx, s0);
+              if (key + 1 < jb.nk) mx = fmaxf(mx, s1);
+              const float p0 = key < jb.nk ? ex2_approx(fmaf(s0, sl2, -mb)) : 0.f;
+              const float p1 = key + 1 < jb.nk ? ex2_approx(fmaf(s1, sl2, -mb)) : 0.f;
+              hv[i] = __floats2half2_rn(p0, p1);
+              sum += p0 + p1;
+            }
+          }
+          uint8_t* tile = prow + (c >> 1) * TILE_BYTES;
+          const int ch0 = (c & 1) * 4;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(tile + (((ch0 + g) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[g];
         }
-      }
-      const long long t2 = dbgt ? clock64() : 0;
-      float corr = 1.f;
-      if (LAZY) {
-        // PV(j-1) has retired: the P tiles may be overwritten and O is stable for a rescale
-        if (j > 0) { mbar_wait(o_full, (j - 1) & 1); tc_fence_after(); }
-        const bool grow = j == 0 || (mx - m_run) * sl2 > 8.f;        // scale reference too small for this chunk
-        if (j == 0) {
-          m_run = mx;
-        } else if (__any_sync(0xffffffffu, grow)) {
+      };
+      float corr = 1.f, sum = 0.f;
+      long long t2 = t1;
+      if (LAZY && j > 0) {
+        // PV(j-1) has retired (it precedes S(j) on the tensor pipe): the P tiles may be overwritten, O is stable.
+        // SINGLE sweep with the current scaling reference m_run; only if some row's maximum outgrew it by 2^8 (rare
+        // after the first chunk) is O rescaled in TMEM and the sweep repeated with the new reference.
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        float mx = -INFINITY;
+        sweep(m_run * sl2, sum, mx);
+        t2 = dbgt ? clock64() : 0;
+        const bool grow = (mx - m_run) * sl2 > 8.f;
+        if (__any_sync(0xffffffffu, grow)) {
           if (grow) { corr = ex2_approx((m_run - mx) * sl2); m_run = mx; l_run *= corr; }
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -182,44 +210,37 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
             tmem_st32(tl + 128 + c * 32, r);
           }
           tmem_st_wait();
+          sum = 0.f;
+          float unused = -INFINITY;
+          sweep(m_run * sl2, sum, unused);
         }
       } else {
-        const float m_new = fmaxf(m_run, mx);               // finite: every chunk holds >= 1 valid key
-        corr = ex2_approx((m_run - m_new) * sl2);
-        m_run = m_new;
-        l_run *= corr;
-      }
-      const float mb = m_run * sl2;
-      float sum = 0.f;
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < ngrp; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tl + c * 32, r);
-        tmem_ld_wait();
-        __align__(16) __half2 hv[16];
-        if (kbase + c * 32 + 32 <= jb.nk) {                 // full 32-key group (warp-uniform): no masking
+        for (int c = 0; c < ngrp; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tl + c * 32, r);
+          tmem_ld_wait();
+          if (kbase + c * 32 + 32 <= jb.nk) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb));
-            hv[i] = __floats2half2_rn(p0, p1);
-            sum += p0 + p1;
-          }
-        } else {
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int key = kbase + c * 32 + 2 * i;
-            const float p0 = key < jb.nk ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), sl2, -mb)) : 0.f;
-            const float p1 = key + 1 < jb.nk ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb)) : 0.f;
-            hv[i] = __floats2half2_rn(p0, p1);
-            sum += p0 + p1;
+            for (int i = 0; i < 32; ++i)
+              if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
           }
         }
-        uint8_t* tile = prow + (c >> 1) * TILE_BYTES;
-        const int ch0 = (c & 1) * 4;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<uint4*>(tile + (((ch0 + g) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[g];
+        t2 = dbgt ? clock64() : 0;
+        if (LAZY) {
+          m_run = mx;                                         // first chunk: the reference is its own maximum
+        } else {
+          const float m_new = fmaxf(m_run, mx);               // finite: every chunk holds >= 1 valid key
+          corr = ex2_approx((m_run - m_new) * sl2);
+          m_run = m_new;
+          l_run *= corr;
+        }
+        float unused = -INFINITY;
+        sweep(m_run * sl2, sum, unused);
       }
       l_run += sum;
       fence_proxy_async_smem();
