@@ -59,3 +59,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 txt = open(os.path.join(root, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/dvins_perception.h must compile as C99 (no C++ / torch / CUDA types)."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "dvins_perception.h"\nint main(void) { dv_config c; dv_config_default(&c); return (int)c.struct_size == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_cpp_shim_compiles_against_the_header(tmp_path):
+    """The reference-facing C++ facade (same class / member names as deep_net.h) builds with g++ alone - no CUDA, no
+    torch - and links against the C-ABI library."""
+    import subprocess
+    from d_vins_b200 import build
+    lib = build.build()
+    obj = tmp_path / "shim.o"
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-c", os.path.join(ROOT, "d_vins_b200", "csrc", "shim", "deep_net_shim.cpp"),
+                        "-I", os.path.join(ROOT, "include"), "-o", str(obj)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exe = build.build_shim_demo()
+    assert os.path.exists(exe) and os.path.exists(lib)
