@@ -179,3 +179,49 @@ def test_mix_preprocess_matches_compiled_reference_golden():
         o = omix.preprocess_mix(g[tag + "_img"])
         assert np.array_equal(o, g[tag + "_ieee"])
         assert len(g[tag + "_fast_levels_diff"]) < 2e-3 * o.size
+
+
+def test_mixvpr_aggregator_matches_published_module_form(all_weights):
+    """amaralibey/MixVPR is not vendored in the reference (README.md:35-45 only names its config).  The oracle's functional
+    aggregator is checked against the published module structure restated as nn.Modules - FeatureMixerLayer =
+    x + Sequential(LayerNorm, Linear, ReLU, Linear)(x); MixVPR = flatten(2) -> mix -> permute -> channel_proj -> permute ->
+    row_proj -> L2-normalise(flatten(1)) - loaded STRICTLY from the same state_dict keys the real checkpoint uses
+    (`aggregator.mix.{i}.mix.{0,1,3}`, `aggregator.channel_proj`, `aggregator.row_proj`)."""
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import mixvpr as omix, weights
+
+    class FeatureMixerLayer(nn.Module):
+        def __init__(self, in_dim, mlp_ratio=1):
+            super().__init__()
+            self.mix = nn.Sequential(nn.LayerNorm(in_dim), nn.Linear(in_dim, int(in_dim * mlp_ratio)), nn.ReLU(),
+                                     nn.Linear(int(in_dim * mlp_ratio), in_dim))
+
+        def forward(self, x):
+            return x + self.mix(x)
+
+    class MixVPR(nn.Module):
+        def __init__(self, in_channels=1024, in_h=20, in_w=20, out_channels=256, mix_depth=4, mlp_ratio=1, out_rows=2):
+            super().__init__()
+            hw = in_h * in_w
+            self.mix = nn.Sequential(*[FeatureMixerLayer(hw, mlp_ratio) for _ in range(mix_depth)])
+            self.channel_proj = nn.Linear(in_channels, out_channels)
+            self.row_proj = nn.Linear(hw, out_rows)
+
+        def forward(self, x):
+            x = self.mix(x.flatten(2))
+            x = self.channel_proj(x.permute(0, 2, 1)).permute(0, 2, 1)
+            x = self.row_proj(x)
+            return F.normalize(x.flatten(1), p=2, dim=-1)
+
+    wm = weights.sub(all_weights, "mix.")
+    agg = MixVPR().eval()
+    sd = {k[len("aggregator."):]: torch.from_numpy(v) for k, v in wm.items() if k.startswith("aggregator.")}
+    agg.load_state_dict(sd, strict=True)                       # key names and shapes are exactly the module's
+    feat = torch.from_numpy(np.random.default_rng(4).standard_normal((1, 1024, 20, 20)).astype(np.float32)).relu()
+    with torch.no_grad():
+        ref = agg(feat)[0].numpy()
+        got = omix.aggregator(wm, feat).numpy()
+    assert ref.shape == (512,)
+    assert np.abs(ref - got).max() < 1e-6
