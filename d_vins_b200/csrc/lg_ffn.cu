@@ -40,7 +40,21 @@ struct FfnParams {
   __half* x16; int ld16;       // fp16 copy of x (X2[:, 0:256], ld 512)
 };
 
-__device__ __forceinline__ float gelu_erf(float y) { return 0.5f * y * (1.f + erff(y * 0.70710678118654752f)); }
+// exact (erf) GELU via Abramowitz-Stegun 7.1.26 on bare MUFU rcp / ex2 (|error| 3e-7; see lg.cu): ~17 instructions
+// instead of the ~50 of libm's erff - the E1 pass of this kernel is issue-bound on exactly this.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_z = poly * t * e;
+  const float half_x = 0.5f * x;
+  return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
+}
 
 __global__ void __launch_bounds__(320, 1) lg_ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX,
                                                               const __grid_constant__ CUtensorMap tmW0,
@@ -168,9 +182,12 @@ __global__ void __launch_bounds__(320, 1) lg_ffn_fused_kernel(const __grid_const
         tmem_ld32(tlane + col0, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(r[j]) + par[col0 + j];
-          s1 += v; s2 = fmaf(v, v, s2);
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&par[col0 + g * 4]);      // broadcast
+          const float v0 = __uint_as_float(r[g * 4]) + b4.x, v1 = __uint_as_float(r[g * 4 + 1]) + b4.y;
+          const float v2 = __uint_as_float(r[g * 4 + 2]) + b4.z, v3 = __uint_as_float(r[g * 4 + 3]) + b4.w;
+          s1 += (v0 + v1) + (v2 + v3);
+          s2 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, s2))));
         }
       }
       stat[row * 2 + half] = make_float2(s1, s2);
@@ -178,7 +195,8 @@ __global__ void __launch_bounds__(320, 1) lg_ffn_fused_kernel(const __grid_const
       const float2 o = stat[row * 2 + (half ^ 1)];
       const float mean = (s1 + o.x) * (1.f / 512.f);
       const float var = fmaxf((s2 + o.y) * (1.f / 512.f) - mean * mean, 0.f);
-      const float rstd = 1.f / sqrtf(var + 1e-5f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const float nmr = -mean * rstd;
       // ---- E1 pass B: normalise, GELU, fp16 -> H (SWIZZLE_128B K-major tiles of 64 columns)
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
@@ -188,12 +206,18 @@ __global__ void __launch_bounds__(320, 1) lg_ffn_fused_kernel(const __grid_const
         tmem_ld_wait();
         __align__(16) __half2 hv[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k0 = col0 + 2 * j;
-          const float v0 = __uint_as_float(r[2 * j]) + par[k0], v1 = __uint_as_float(r[2 * j + 1]) + par[k0 + 1];
-          const float y0 = (v0 - mean) * rstd * par[512 + k0] + par[1024 + k0];
-          const float y1 = (v1 - mean) * rstd * par[512 + k0 + 1] + par[1024 + k0 + 1];
-          hv[j] = __floats2half2_rn(gelu_erf(y0), gelu_erf(y1));
+        for (int g = 0; g < 8; ++g) {
+          const int k0 = col0 + g * 4;
+          const float4 b4 = *reinterpret_cast<const float4*>(&par[k0]);                 // b0, gamma, beta: broadcast
+          const float4 g4 = *reinterpret_cast<const float4*>(&par[512 + k0]);
+          const float4 e4 = *reinterpret_cast<const float4*>(&par[1024 + k0]);
+          // ((v - mean) * rstd) * gamma + beta as two FMAs
+          const float y0 = fmaf(fmaf(__uint_as_float(r[g * 4]) + b4.x, rstd, nmr), g4.x, e4.x);
+          const float y1 = fmaf(fmaf(__uint_as_float(r[g * 4 + 1]) + b4.y, rstd, nmr), g4.y, e4.y);
+          const float y2 = fmaf(fmaf(__uint_as_float(r[g * 4 + 2]) + b4.z, rstd, nmr), g4.z, e4.z);
+          const float y3 = fmaf(fmaf(__uint_as_float(r[g * 4 + 3]) + b4.w, rstd, nmr), g4.w, e4.w);
+          hv[g * 2] = __floats2half2_rn(gelu_erf(y0), gelu_erf(y1));
+          hv[g * 2 + 1] = __floats2half2_rn(gelu_erf(y2), gelu_erf(y3));
         }
         uint8_t* tile = smem + OFF_H + (col0 >> 6) * 16384 + row * 128;
         const int ch0 = (col0 & 63) >> 3;                              // first 16-byte chunk of this 32-column group
