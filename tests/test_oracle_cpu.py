@@ -225,3 +225,53 @@ def test_mixvpr_aggregator_matches_published_module_form(all_weights):
         got = omix.aggregator(wm, feat).numpy()
     assert ref.shape == (512,)
     assert np.abs(ref - got).max() < 1e-6
+
+
+def test_filter_matches_properties_randomised():
+    """Size-independent properties of the match extraction (filter_matches + LightGlue-ONNX packing): every emitted pair
+    is a mutual argmax above the threshold, i0 ascending, no keypoint of either image used twice, nothing valid left out."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import lightglue as olg
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+    def check(m, n, seed):
+        rng = np.random.default_rng(seed)
+        L = np.log(rng.uniform(1e-4, 1.0, (m, n))).astype(np.float32)
+        if seed % 3 == 0:                                   # plant exact ties: lowest index must win on both axes
+            L[:, n // 2] = L[:, 0]
+            L[m // 2, :] = L[0, :]
+        pairs, ms = olg.filter_matches(L)
+        assert np.all(np.diff(pairs[:, 0]) > 0)
+        assert len(set(pairs[:, 1].tolist())) == len(pairs)
+        m0, m1 = L.argmax(1), L.argmax(0)
+        for (i, j), s in zip(pairs, ms):
+            assert m0[i] == j and m1[j] == i and s > np.float32(0.1) and np.isclose(s, np.exp(L[i, j]), rtol=1e-6)
+        valid = [(i, int(m0[i])) for i in range(m) if m1[m0[i]] == i and np.exp(L[i, m0[i]]) > np.float32(0.1)]
+        assert [tuple(p) for p in pairs.tolist()] == valid
+    check()
+
+
+def test_knn_window_and_bruteforce_randomised():
+    """kNN over the bank prefix the reference searches (keyframe.cpp:274-294): ids equal a brute-force sort with the
+    lowest-index tie rule, padded with (-inf, -1) when fewer than k rows are visible."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import knn
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 130), st.integers(0, 2 ** 31 - 1))
+    def check(t, seed):
+        rng = np.random.default_rng(seed)
+        bank = rng.standard_normal((t + 1, 512)).astype(np.float32)
+        bank /= np.linalg.norm(bank, axis=1, keepdims=True)
+        if t > 3:
+            bank[1] = bank[0]                                # duplicate rows: the lower index must rank first
+        q = bank[t]
+        nb = knn.nb_limit(t)
+        assert nb == (t - 49 if t >= 50 else t + 1)
+        D, I = knn.knn_ip(bank, q, nb)
+        sims = bank[:nb] @ q
+        order = sorted(range(nb), key=lambda r: (-sims[r], r))[:3]
+        assert list(I[:len(order)]) == order
+        assert all(i == -1 for i in I[len(order):]) and all(d == -np.inf for d in D[len(order):])
+    check()
