@@ -191,9 +191,12 @@ class Engine:
         _chk(_lib.dv_batch_commit(self._h, b, C.byref(r)))
         return r.value
 
-    def batch_search(self, nb_limit):
-        nb = np.ascontiguousarray(nb_limit, dtype=np.int64)
-        b = nb.shape[0]; k = self.cfg.knn_k
+    def batch_search(self, nb_limit=None, b=None):
+        """nb_limit [b] explicit windows, or None (+ b): the engine applies keyframe.cpp:274-282 with cfg.exclude_recent
+        to the bank rows the last batch_commit assigned."""
+        nb = None if nb_limit is None else np.ascontiguousarray(nb_limit, dtype=np.int64)
+        b = nb.shape[0] if nb is not None else int(b)
+        k = self.cfg.knn_k
         D = np.zeros((b, k), np.float32); I = np.zeros((b, k), np.int64)
         _chk(_lib.dv_batch_search(self._h, b, _ptr(nb, C.c_int64), _ptr(D, C.c_float), _ptr(I, C.c_int64)))
         return D, I
@@ -204,7 +207,40 @@ class Engine:
         ma = np.zeros((b, cap, 2), np.int32); ms = np.zeros((b, cap), np.float32); ko = np.zeros((b,), np.int32)
         _chk(_lib.dv_batch_match(self._h, b, _ptr(q, C.c_int64), _ptr(o, C.c_int64), _ptr(ma, C.c_int32),
                                  _ptr(ms, C.c_float), _ptr(ko, C.c_int32)))
-        return [(ma[i, :ko[i]], ms[i, :ko[i]]) for i in range(b)]
+        self.last_match_status = ko.copy()      # -1: a keyframe of the pair is not resident on any rank
+        return [(ma[i, :max(ko[i], 0)], ms[i, :max(ko[i], 0)]) for i in range(b)]
+
+    def batch_match_ex(self, query_ids, old_ids, query_part=0, old_part=2, cap=None):
+        """query_part / old_part: 0 window points, 1 SuperPoint points, 2 all (dvins_perception.h DV_PART_*)."""
+        q = np.ascontiguousarray(query_ids, dtype=np.int64); o = np.ascontiguousarray(old_ids, dtype=np.int64)
+        b = q.shape[0]; cap = cap or (self.cfg.max_kpts + self.cfg.max_vio)
+        ma = np.zeros((b, cap, 2), np.int32); ms = np.zeros((b, cap), np.float32); ko = np.zeros((b,), np.int32)
+        _chk(_lib.dv_batch_match_ex(self._h, b, _ptr(q, C.c_int64), _ptr(o, C.c_int64), int(query_part), int(old_part),
+                                    int(cap), _ptr(ma, C.c_int32), _ptr(ms, C.c_float), _ptr(ko, C.c_int32)))
+        self.last_match_status = ko.copy()
+        return [(ma[i, :max(ko[i], 0)], ms[i, :max(ko[i], 0)]) for i in range(b)]
+
+    def batch_match_sp(self, query_ids, old_ids):
+        """SuperPoint-vs-SuperPoint pair match (BASELINE config 2)."""
+        return self.batch_match_ex(query_ids, old_ids, 1, 1, self.cfg.max_kpts)
+
+    def batch_describe_global(self, b):
+        _chk(_lib.dv_batch_describe_global(self._h, int(b)))
+
+    def store_lookup_many(self, frame_ids):
+        ids = np.ascontiguousarray(frame_ids, dtype=np.int64)
+        out = np.full((ids.shape[0],), -1, np.int32)
+        _chk(_lib.dv_store_lookup_many(self._h, int(ids.shape[0]), _ptr(ids, C.c_int64), _ptr(out, C.c_int32)))
+        return out
+
+    def store_lookup(self, frame_id):
+        """-> (owner_rank or -1, n_total, n_sp)"""
+        r = C.c_int32(-1); n = C.c_int32(0); nsp = C.c_int32(0)
+        _chk(_lib.dv_store_lookup(self._h, C.c_int64(frame_id), C.byref(r), C.byref(n), C.byref(nsp)))
+        return r.value, n.value, nsp.value
+
+    def store_sync(self):
+        _chk(_lib.dv_store_sync(self._h))
 
     def store_read(self, frame_id):
         cap = self.cfg.max_kpts + self.cfg.max_vio
@@ -290,6 +326,9 @@ class Engine:
 
     def probe_enable(self, on=True):
         _chk(_lib.dv_probe_enable(self._h, 1 if on else 0))
+
+    def probe_select(self, which):
+        _chk(_lib.dv_probe_select(self._h, int(which)))
 
     def probe_read(self, reset=True):
         ms = C.c_double(0); n = C.c_int64(0)

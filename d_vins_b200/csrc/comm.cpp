@@ -18,6 +18,8 @@ struct Comm {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
 };
 
 static Comm* g_api = nullptr;   // function table shared by all engines of the process
@@ -34,6 +36,8 @@ static int load_api() {
   c->AllGather = reinterpret_cast<decltype(c->AllGather)>(dlsym(lib, "ncclAllGather"));
   c->CommDestroy = reinterpret_cast<decltype(c->CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
   c->GetErrorString = reinterpret_cast<decltype(c->GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  c->CommGetAsyncError = reinterpret_cast<decltype(c->CommGetAsyncError)>(dlsym(lib, "ncclCommGetAsyncError"));
+  c->CommAbort = reinterpret_cast<decltype(c->CommAbort)>(dlsym(lib, "ncclCommAbort"));
   if (!c->GetUniqueId || !c->CommInitRank || !c->AllGather || !c->CommDestroy) {
     delete c;
     set_error("libnccl is missing required symbols");
@@ -59,6 +63,21 @@ int comm_allgather_bytes(Engine* e, const void* send, void* recv, size_t bytes_p
   if (!e->comm || !e->comm->comm) { set_error("world_size > 1 but dv_comm_init was not called"); return DV_ERR_COMM; }
   ncclResult_t r = g_api->AllGather(send, recv, bytes_per_rank, ncclInt8, e->comm->comm, e->st);
   if (r != ncclSuccess) return nccl_fail("ncclAllGather", r);
+  return DV_OK;
+}
+
+// Failure detection: NCCL reports network / peer failures asynchronously; every collective of the path is
+// followed (after its stream synchronisation) by this non-blocking query, so a dead peer surfaces as DV_ERR_COMM on the
+// call that used the collective instead of a hang or silently stale bank rows.
+int comm_poll(Engine* e) {
+  if (!e->comm || !e->comm->comm || !g_api || !g_api->CommGetAsyncError) return DV_OK;
+  ncclResult_t async = ncclSuccess;
+  ncclResult_t r = g_api->CommGetAsyncError(e->comm->comm, &async);
+  if (r != ncclSuccess) return nccl_fail("ncclCommGetAsyncError", r);
+  if (async != ncclSuccess && async != ncclInProgress) {
+    if (g_api->CommAbort) { g_api->CommAbort(e->comm->comm); e->comm->comm = nullptr; }
+    return nccl_fail("NCCL asynchronous error (communicator aborted)", async);
+  }
   return DV_OK;
 }
 

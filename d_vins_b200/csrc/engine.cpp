@@ -14,6 +14,19 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* get_error() { return g_err.c_str(); }
 
+// Device scratch of the dv_dbg_* entry points: released on every return path (DV_CUDA_OK returns early on failure).
+struct Scratch {
+  std::vector<void*> bufs;
+  ~Scratch() { for (void* q : bufs) cudaFree(q); }
+  template <class T> cudaError_t get(T** out, size_t bytes) {
+    void* q = nullptr;
+    const cudaError_t err = cudaMalloc(&q, bytes);
+    if (err == cudaSuccess) bufs.push_back(q);
+    *out = reinterpret_cast<T*>(q);
+    return err;
+  }
+};
+
 static int drain_stats(Engine* e) {
   for (auto& p : e->pending) {
     float ms = 0.f;
@@ -77,8 +90,17 @@ dv_status dv_create(const dv_config* cfg, dv_engine** out) {
   if (cfg->height < 64 || cfg->width < 64 || cfg->max_batch < 1 || cfg->max_kpts < 1 || cfg->max_kpts > 1024 ||
       cfg->max_vio < 1 || cfg->max_vio > 512 || cfg->lg_max_kpts < 16 || cfg->lg_max_kpts > 2048 ||
       cfg->knn_k < 1 || cfg->knn_k > 8 || cfg->nms_radius != 4 || cfg->world_size < 1 || cfg->rank < 0 ||
-      cfg->rank >= cfg->world_size || cfg->bank_capacity < 1 || cfg->store_capacity < 1) {
+      cfg->rank >= cfg->world_size || cfg->bank_capacity < 1 || cfg->store_capacity < 1 || cfg->exclude_recent < 0) {
     set_error("dv_create: configuration out of the supported range");
+    return DV_ERR_UNSUPPORTED;
+  }
+  // LightGlue sees max_vio window points on the query side and max_kpts + max_vio points on the old keyframe's side
+  if (cfg->max_vio > cfg->lg_max_kpts || cfg->max_kpts + cfg->max_vio > cfg->lg_max_kpts) {
+    set_error("dv_create: need max_kpts + max_vio <= lg_max_kpts (LightGlue token capacity per image)");
+    return DV_ERR_UNSUPPORTED;
+  }
+  if (cfg->store_capacity < cfg->max_batch) {
+    set_error("dv_create: store_capacity must hold at least one batch (max_batch keyframes)");
     return DV_ERR_UNSUPPORTED;
   }
   DV_CUDA_OK(cudaSetDevice(cfg->device));
@@ -191,6 +213,12 @@ dv_status dv_probe_enable(dv_engine* h, int32_t on) {
   reinterpret_cast<Engine*>(h)->probe_on = on != 0;
   return DV_OK;
 }
+dv_status dv_probe_select(dv_engine* h, int32_t which) {
+  DV_CHECK_ENGINE(h);
+  if (which < 0 || which > 1) { set_error("dv_probe_select: 0 = conv1a+conv1b kernel, 1 = kNN scan"); return DV_ERR_INVALID; }
+  reinterpret_cast<Engine*>(h)->probe_sel = which;
+  return DV_OK;
+}
 dv_status dv_probe_read(dv_engine* h, double* ms, int64_t* launches, int32_t reset) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
@@ -215,21 +243,22 @@ dv_status dv_dbg_gemm(dv_engine* h, const float* A, const float* Bm, const float
                       int32_t relu, float* D) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
+  Scratch sc;
   if (!A || !Bm || !D || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 4)) {
     set_error("dv_dbg_gemm: need K % 8 == 0, N % 4 == 0");
     return DV_ERR_INVALID;
   }
   float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr, *dbias = nullptr;
   __half *dA = nullptr, *dB = nullptr;
-  DV_CUDA_OK(cudaMalloc(&dA32, (size_t)M * K * 4));
-  DV_CUDA_OK(cudaMalloc(&dB32, (size_t)N * K * 4));
-  DV_CUDA_OK(cudaMalloc(&dA, (size_t)M * K * 2));
-  DV_CUDA_OK(cudaMalloc(&dB, (size_t)N * K * 2));
-  DV_CUDA_OK(cudaMalloc(&dD, (size_t)M * N * 4));
+  DV_CUDA_OK(sc.get(&dA32, (size_t)M * K * 4));
+  DV_CUDA_OK(sc.get(&dB32, (size_t)N * K * 4));
+  DV_CUDA_OK(sc.get(&dA, (size_t)M * K * 2));
+  DV_CUDA_OK(sc.get(&dB, (size_t)N * K * 2));
+  DV_CUDA_OK(sc.get(&dD, (size_t)M * N * 4));
   DV_CUDA_OK(cudaMemcpyAsync(dA32, A, (size_t)M * K * 4, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dB32, Bm, (size_t)N * K * 4, cudaMemcpyHostToDevice, e->st));
   if (bias) {
-    DV_CUDA_OK(cudaMalloc(&dbias, (size_t)N * 4));
+    DV_CUDA_OK(sc.get(&dbias, (size_t)N * 4));
     DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice, e->st));
   }
   f32_to_f16(dA32, dA, (int64_t)M * K, e->st);
@@ -244,7 +273,6 @@ dv_status dv_dbg_gemm(dv_engine* h, const float* A, const float* Bm, const float
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
     if (ce != cudaSuccess) { set_error(std::string("dv_dbg_gemm: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
   }
-  cudaFree(dA32); cudaFree(dB32); cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dbias);
   return (dv_status)rc;
 }
 
@@ -252,6 +280,7 @@ dv_status dv_dbg_gemm_ex(dv_engine* h, const float* A, const float* Bm, const fl
                          int32_t res_is_f16, int32_t M, int32_t N, int32_t K, int32_t relu, float* D32, float* D16) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
+  Scratch sc;
   if (!A || !Bm || (!D32 && !D16) || M <= 0 || N <= 0 || K <= 0 || (K % 8) || (N % 8)) {
     set_error("dv_dbg_gemm_ex: need K % 8 == 0, N % 8 == 0 and at least one output");
     return DV_ERR_INVALID;
@@ -259,18 +288,18 @@ dv_status dv_dbg_gemm_ex(dv_engine* h, const float* A, const float* Bm, const fl
   const size_t mk = (size_t)M * K, nk = (size_t)N * K, mn = (size_t)M * N;
   float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr, *dbias = nullptr, *dtmp = nullptr;
   __half *dA = nullptr, *dB = nullptr, *dD16 = nullptr, *dR16 = nullptr;
-  DV_CUDA_OK(cudaMalloc(&dA32, mk * 4));
-  DV_CUDA_OK(cudaMalloc(&dB32, nk * 4));
-  DV_CUDA_OK(cudaMalloc(&dA, mk * 2));
-  DV_CUDA_OK(cudaMalloc(&dB, nk * 2));
-  DV_CUDA_OK(cudaMalloc(&dD, mn * 4));
-  DV_CUDA_OK(cudaMalloc(&dtmp, mn * 4));
-  DV_CUDA_OK(cudaMalloc(&dD16, mn * 2));
-  DV_CUDA_OK(cudaMalloc(&dR16, mn * 2));
+  DV_CUDA_OK(sc.get(&dA32, mk * 4));
+  DV_CUDA_OK(sc.get(&dB32, nk * 4));
+  DV_CUDA_OK(sc.get(&dA, mk * 2));
+  DV_CUDA_OK(sc.get(&dB, nk * 2));
+  DV_CUDA_OK(sc.get(&dD, mn * 4));
+  DV_CUDA_OK(sc.get(&dtmp, mn * 4));
+  DV_CUDA_OK(sc.get(&dD16, mn * 2));
+  DV_CUDA_OK(sc.get(&dR16, mn * 2));
   DV_CUDA_OK(cudaMemcpyAsync(dA32, A, mk * 4, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dB32, Bm, nk * 4, cudaMemcpyHostToDevice, e->st));
   if (bias) {
-    DV_CUDA_OK(cudaMalloc(&dbias, (size_t)N * 4));
+    DV_CUDA_OK(sc.get(&dbias, (size_t)N * 4));
     DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)N * 4, cudaMemcpyHostToDevice, e->st));
   }
   f32_to_f16(dA32, dA, (int64_t)mk, e->st);
@@ -304,8 +333,6 @@ dv_status dv_dbg_gemm_ex(dv_engine* h, const float* A, const float* Bm, const fl
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
     if (ce != cudaSuccess) { set_error(std::string("dv_dbg_gemm_ex: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
   }
-  cudaFree(dA32); cudaFree(dB32); cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dbias); cudaFree(dtmp);
-  cudaFree(dD16); cudaFree(dR16);
   return (dv_status)rc;
 }
 
@@ -313,6 +340,7 @@ dv_status dv_dbg_conv3x3(dv_engine* h, const float* x, const float* wgt, const f
                          int32_t ww, int32_t cin, int32_t cout, int32_t relu, int32_t pool, float* y) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
+  Scratch sc;
   if (!x || !wgt || !y || n <= 0 || hh <= 0 || ww <= 0 || (cin % 64) || (cout % 8)) {
     set_error("dv_dbg_conv3x3: need cin % 64 == 0, cout % 8 == 0");
     return DV_ERR_INVALID;
@@ -327,14 +355,14 @@ dv_status dv_dbg_conv3x3(dv_engine* h, const float* x, const float* wgt, const f
       for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * cin + c] = wgt[((size_t)o * cin + c) * 9 + t];
   float *dx32 = nullptr, *dw32 = nullptr, *dy32 = nullptr, *dbias = nullptr;
   __half *dx = nullptr, *dw = nullptr, *dy = nullptr;
-  DV_CUDA_OK(cudaMalloc(&dx32, nx * 4)); DV_CUDA_OK(cudaMalloc(&dx, nx * 2));
-  DV_CUDA_OK(cudaMalloc(&dw32, wr.size() * 4)); DV_CUDA_OK(cudaMalloc(&dw, wr.size() * 2));
-  DV_CUDA_OK(cudaMalloc(&dy, ny * 2)); DV_CUDA_OK(cudaMalloc(&dy32, ny * 4));
+  DV_CUDA_OK(sc.get(&dx32, nx * 4)); DV_CUDA_OK(sc.get(&dx, nx * 2));
+  DV_CUDA_OK(sc.get(&dw32, wr.size() * 4)); DV_CUDA_OK(sc.get(&dw, wr.size() * 2));
+  DV_CUDA_OK(sc.get(&dy, ny * 2)); DV_CUDA_OK(sc.get(&dy32, ny * 4));
   DV_CUDA_OK(cudaMemsetAsync(dy, 0, ny * 2, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dx32, x, nx * 4, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dw32, wr.data(), wr.size() * 4, cudaMemcpyHostToDevice, e->st));
   if (bias) {
-    DV_CUDA_OK(cudaMalloc(&dbias, (size_t)cout * 4));
+    DV_CUDA_OK(sc.get(&dbias, (size_t)cout * 4));
     DV_CUDA_OK(cudaMemcpyAsync(dbias, bias, (size_t)cout * 4, cudaMemcpyHostToDevice, e->st));
   }
   f32_to_f16(dx32, dx, (int64_t)nx, e->st);
@@ -350,7 +378,6 @@ dv_status dv_dbg_conv3x3(dv_engine* h, const float* x, const float* wgt, const f
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
     if (ce != cudaSuccess) { set_error(std::string("dv_dbg_conv3x3: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
   }
-  cudaFree(dx32); cudaFree(dx); cudaFree(dw32); cudaFree(dw); cudaFree(dy); cudaFree(dy32); cudaFree(dbias);
   return (dv_status)rc;
 }
 
@@ -358,6 +385,7 @@ dv_status dv_dbg_conv3x3_halo64(dv_engine* h, const float* x, const float* wgt, 
                                 int32_t ww, int32_t relu, int32_t pool, int32_t out_blocked, float* y) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
+  Scratch sc;
   if (!x || !wgt || !bias || !y || n <= 0 || hh <= 0 || ww <= 0) { set_error("dv_dbg_conv3x3_halo64: bad argument"); return DV_ERR_INVALID; }
   const int C = 64;
   const size_t nx = (size_t)n * hh * ww * C;
@@ -374,10 +402,10 @@ dv_status dv_dbg_conv3x3_halo64(dv_engine* h, const float* x, const float* wgt, 
       for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * C + c] = wgt[((size_t)o * C + c) * 9 + t];
   float *dx32 = nullptr, *dw32 = nullptr, *dy32 = nullptr, *dbias = nullptr;
   __half *dx = nullptr, *dw = nullptr, *dy = nullptr;
-  DV_CUDA_OK(cudaMalloc(&dx32, nx * 4)); DV_CUDA_OK(cudaMalloc(&dx, nx * 2));
-  DV_CUDA_OK(cudaMalloc(&dw32, wr.size() * 4)); DV_CUDA_OK(cudaMalloc(&dw, wr.size() * 2));
-  DV_CUDA_OK(cudaMalloc(&dy, ny * 2 + 64)); DV_CUDA_OK(cudaMalloc(&dy32, ny * 4));
-  DV_CUDA_OK(cudaMalloc(&dbias, C * 4));
+  DV_CUDA_OK(sc.get(&dx32, nx * 4)); DV_CUDA_OK(sc.get(&dx, nx * 2));
+  DV_CUDA_OK(sc.get(&dw32, wr.size() * 4)); DV_CUDA_OK(sc.get(&dw, wr.size() * 2));
+  DV_CUDA_OK(sc.get(&dy, ny * 2 + 64)); DV_CUDA_OK(sc.get(&dy32, ny * 4));
+  DV_CUDA_OK(sc.get(&dbias, C * 4));
   DV_CUDA_OK(cudaMemsetAsync(dy, 0, ny * 2, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dx32, xb.data(), nx * 4, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dw32, wr.data(), wr.size() * 4, cudaMemcpyHostToDevice, e->st));
@@ -393,7 +421,6 @@ dv_status dv_dbg_conv3x3_halo64(dv_engine* h, const float* x, const float* wgt, 
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
     if (ce != cudaSuccess) { set_error(std::string("dv_dbg_conv3x3_halo64: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
   }
-  cudaFree(dx32); cudaFree(dx); cudaFree(dw32); cudaFree(dw); cudaFree(dy); cudaFree(dy32); cudaFree(dbias);
   if (rc) return (dv_status)rc;
   if (out_blocked) {
     for (int b = 0; b < n; ++b)
@@ -412,6 +439,7 @@ dv_status dv_dbg_conv3x3_halo128(dv_engine* h, const float* x, const float* wgt,
                                  float* y) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
+  Scratch sc;
   if (!x || !wgt || !bias || !y || n <= 0 || hh <= 0 || ww <= 0) { set_error("dv_dbg_conv3x3_halo128: bad argument"); return DV_ERR_INVALID; }
   const size_t nx = (size_t)n * hh * ww * cin;
   const int ho = pool ? hh / 2 : hh, wo = pool ? ww / 2 : ww;
@@ -427,10 +455,10 @@ dv_status dv_dbg_conv3x3_halo128(dv_engine* h, const float* x, const float* wgt,
       for (int t = 0; t < 9; ++t) wr[((size_t)o * 9 + t) * cin + c] = wgt[((size_t)o * cin + c) * 9 + t];
   float *dx32 = nullptr, *dw32 = nullptr, *dy32 = nullptr, *dbias = nullptr;
   __half *dx = nullptr, *dw = nullptr, *dy = nullptr;
-  DV_CUDA_OK(cudaMalloc(&dx32, nx * 4)); DV_CUDA_OK(cudaMalloc(&dx, nx * 2));
-  DV_CUDA_OK(cudaMalloc(&dw32, wr.size() * 4)); DV_CUDA_OK(cudaMalloc(&dw, wr.size() * 2));
-  DV_CUDA_OK(cudaMalloc(&dy, ny * 2 + 64)); DV_CUDA_OK(cudaMalloc(&dy32, ny * 4));
-  DV_CUDA_OK(cudaMalloc(&dbias, (size_t)cout * 4));
+  DV_CUDA_OK(sc.get(&dx32, nx * 4)); DV_CUDA_OK(sc.get(&dx, nx * 2));
+  DV_CUDA_OK(sc.get(&dw32, wr.size() * 4)); DV_CUDA_OK(sc.get(&dw, wr.size() * 2));
+  DV_CUDA_OK(sc.get(&dy, ny * 2 + 64)); DV_CUDA_OK(sc.get(&dy32, ny * 4));
+  DV_CUDA_OK(sc.get(&dbias, (size_t)cout * 4));
   DV_CUDA_OK(cudaMemsetAsync(dy, 0, ny * 2, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dx32, xb.data(), nx * 4, cudaMemcpyHostToDevice, e->st));
   DV_CUDA_OK(cudaMemcpyAsync(dw32, wr.data(), wr.size() * 4, cudaMemcpyHostToDevice, e->st));
@@ -446,7 +474,6 @@ dv_status dv_dbg_conv3x3_halo128(dv_engine* h, const float* x, const float* wgt,
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
     if (ce != cudaSuccess) { set_error(std::string("dv_dbg_conv3x3_halo128: ") + cudaGetErrorString(ce)); rc = DV_ERR_CUDA; }
   }
-  cudaFree(dx32); cudaFree(dx); cudaFree(dw32); cudaFree(dw); cudaFree(dy); cudaFree(dy32); cudaFree(dbias);
   if (rc) return (dv_status)rc;
   if (out_blocked) {
     for (int b = 0; b < n; ++b)
@@ -464,6 +491,7 @@ dv_status dv_dbg_conv3x3_halo128(dv_engine* h, const float* x, const float* wgt,
 dv_status dv_dbg_read(dv_engine* h, const char* name, float* dst, int64_t capacity, int64_t* count) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
+  Scratch sc;
   auto it = e->dbg.find(name ? name : "");
   if (it == e->dbg.end()) { set_error(std::string("dv_dbg_read: unknown tensor ") + (name ? name : "(null)")); return DV_ERR_INVALID; }
   const Engine::Dbg& d = it->second;
@@ -474,11 +502,10 @@ dv_status dv_dbg_read(dv_engine* h, const char* name, float* dst, int64_t capaci
     DV_CUDA_OK(cudaMemcpyAsync(dst, d.p, (size_t)d.n * 4, cudaMemcpyDeviceToHost, e->st));
   } else {
     float* tmp = nullptr;
-    DV_CUDA_OK(cudaMalloc(&tmp, (size_t)d.n * 4));
+    DV_CUDA_OK(sc.get(&tmp, (size_t)d.n * 4));
     f16_to_f32(reinterpret_cast<const __half*>(d.p), tmp, d.n, e->st);
     cudaError_t ce = cudaMemcpyAsync(dst, tmp, (size_t)d.n * 4, cudaMemcpyDeviceToHost, e->st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->st);
-    cudaFree(tmp);
     if (ce != cudaSuccess) { set_error(std::string("dv_dbg_read: ") + cudaGetErrorString(ce)); return DV_ERR_CUDA; }
   }
   DV_CUDA_OK(cudaStreamSynchronize(e->st));

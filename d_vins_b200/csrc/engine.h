@@ -97,6 +97,7 @@ struct Engine {
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> ev_pool;
   bool probe_on = false;
+  int probe_sel = 0;            // which kernel the probe brackets: 0 conv1a+conv1b implicit GEMM, 1 kNN bank scan
   double probe_ms = 0; int64_t probe_n = 0;
   std::vector<Pending> probe_pending;
 
@@ -132,7 +133,7 @@ struct Engine {
 // stage timing scope (no-op unless stats are enabled)
 struct ProbeScope {   // event pair around one kernel launch (dominant-kernel roofline probe)
   Engine* e; cudaEvent_t a = nullptr, b = nullptr;
-  explicit ProbeScope(Engine* e_);
+  explicit ProbeScope(Engine* e_, int which = 0);
   ~ProbeScope();
 };
 struct StageScope {

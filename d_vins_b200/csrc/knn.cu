@@ -178,9 +178,12 @@ __global__ void __launch_bounds__(256) k_knn_merge(const float* __restrict__ par
 }
 
 template <int K>
-static void knn_launch(const float* rows, const float* q, const long long* d_nb, int nq, int nblocks, float* partD,
+static void knn_launch(Engine* e, const float* rows, const float* q, const long long* d_nb, int nq, int nblocks, float* partD,
                        long long* partI, float* outD, long long* outI, cudaStream_t st) {
-  k_knn_scan<K><<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, st>>>(rows, q, d_nb, nq, partD, partI, nblocks);
+  {
+    ProbeScope pr(e, 1);   // roofline probe of the HBM-bound scan (bench.py --config mix_knn_10k)
+    k_knn_scan<K><<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, st>>>(rows, q, d_nb, nq, partD, partI, nblocks);
+  }
   k_knn_merge<K><<<nq, 256, 0, st>>>(partD, partI, nblocks, outD, outI);
 }
 
@@ -231,14 +234,14 @@ int bank_search_device(Engine* e, int nq, const int64_t* nb_limit, int k, float*
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int nblocks = (int)std::min<int64_t>(cdiv64(maxlim, KNN_ROWS_PER_BLOCK), (int64_t)dev_sms * 2);   // 128 registers x 256 threads: two resident blocks per SM
   switch (k) {
-    case 1: knn_launch<1>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 2: knn_launch<2>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 3: knn_launch<3>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 4: knn_launch<4>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 5: knn_launch<5>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 6: knn_launch<6>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 7: knn_launch<7>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    default: knn_launch<8>(b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 1: knn_launch<1>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 2: knn_launch<2>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 3: knn_launch<3>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 4: knn_launch<4>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 5: knn_launch<5>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 6: knn_launch<6>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    case 7: knn_launch<7>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+    default: knn_launch<8>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
   }
   DV_CUDA_OK(cudaGetLastError());
   DV_LAUNCHED(e, 2);

@@ -776,7 +776,7 @@ static int lg_tail(Engine* e, int P, const PairDesc* d_pd, const LgSeg* d_segs, 
 }
 
 // segs: host array [2P] with device pointers to keypoints / descriptors; results stay on the device.
-int lg_run(Engine* e, int P, const LgSeg* segs_in) {
+int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* after_load) {
   LgNet* g = e->lg;
   if (!g) { set_error("LightGlue not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   if (P < 1 || P > g->P) { set_error("lg_run: pair count exceeds max_batch"); return DV_ERR_CAPACITY; }
@@ -820,6 +820,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in) {
   DV_CUDA_OK(cudaMemcpyAsync(g->ju_cross, g->h_ju + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
   k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
   DV_LAUNCHED(e, 1);
+  if (after_load && *after_load) DV_TRY((*after_load)());
   const dim3 agrid(cdiv(max_n_any, ATT_QT), LG_HEADS, 2 * P);
   for (int i = 0; i < LG_LAYERS; ++i) {
     LgLayer& L = g->L[i];

@@ -2,6 +2,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <functional>
+
 namespace dv {
 
 struct Engine;
@@ -18,7 +20,9 @@ struct LgSeg {
 // tcgen05 attention (lg_attn.cu): operands are windows of the packed qkv buffer [T,768]
 struct AttnJobU { int q_row, nq, k_row, nk, q_col, k_col, v_col, pad; };
 
-int lg_run(Engine* e, int P, const LgSeg* segs);   // segs [2P]: (query, old) per pair; results stay on device
+// segs [2P]: (query, old) per pair; results stay on device.  `after_load` (optional) is invoked right after the kernel
+// that reads the callers' keypoint / descriptor pointers has been queued (store.cu verifies remote reads there).
+int lg_run(Engine* e, int P, const LgSeg* segs, const std::function<int()>* after_load = nullptr);
 int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out);
 int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float* mk0, float* mk1, int32_t* k_out);
 

@@ -65,8 +65,8 @@ StageScope::~StageScope() {
   e->pending.push_back({stage, a, b});
 }
 
-ProbeScope::ProbeScope(Engine* e_) : e(e_) {
-  if (!e->probe_on) return;
+ProbeScope::ProbeScope(Engine* e_, int which) : e(e_) {
+  if (!e->probe_on || e->probe_sel != which) return;
   auto get = [&]() {
     cudaEvent_t ev;
     if (!e->ev_pool.empty()) { ev = e->ev_pool.back(); e->ev_pool.pop_back(); }

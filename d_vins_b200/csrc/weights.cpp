@@ -34,7 +34,7 @@ int load_weight_file(const char* path, WeightMap* out) {
       t.dims.push_back((int)v);
     }
     uint64_t off = 0, nb = 0;
-    if (!rd64(&off) || !rd64(&nb) || off + nb > (uint64_t)sz || nb != (uint64_t)t.numel() * 4) {
+    if (!rd64(&off) || !rd64(&nb) || off > (uint64_t)sz || nb > (uint64_t)sz - off || nb != (uint64_t)t.numel() * 4) {
       set_error("bad tensor extent in weight file: " + name);
       return DV_ERR_WEIGHTS;
     }

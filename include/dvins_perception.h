@@ -129,13 +129,28 @@ dv_status dv_batch_extract(dv_engine* e, int32_t b, const float* vio_xy, const i
 /* Append the b new global descriptors to the bank.  world_size > 1: ONE ncclAllGather of [b,512] per rank, landing
  * rank-major in every rank's bank (row = round_base + rank*b + i).  first_row = row of this rank's frame 0. */
 dv_status dv_batch_commit(dv_engine* e, int32_t b, int64_t* first_row);
-/* kNN for the b query descriptors of this round; nb_limit [b] (keyframe.cpp:274-282: index>=50 ? index-49 : index+1). */
+/* kNN for the b query descriptors of this round; nb_limit [b] (keyframe.cpp:274-282: index>=50 ? index-49 : index+1).
+ * nb_limit == NULL: the engine applies that rule itself with cfg.exclude_recent to the rows dv_batch_commit assigned. */
 dv_status dv_batch_search(dv_engine* e, int32_t b, const int64_t* nb_limit, float* D, int64_t* I);
 /* LightGlue for b pairs: query = frame query_ids[i]'s window points + SP_RE descriptors (kpts0/desc0 of
- * keyframe.cpp:605-618), old = frame old_ids[i]'s full keypoint set.  Both must be resident in THIS rank's store.
- * matches [b, max_vio, 2], mscores [b, max_vio], k_out [b]. */
+ * keyframe.cpp:605-618), old = frame old_ids[i]'s full keypoint set.  A keyframe that lives in ANOTHER rank's store is
+ * read in place over NVLink (CUDA-IPC mapping set up by dv_comm_init; seqlock-verified against concurrent slot reuse).
+ * matches [b, max_vio, 2], mscores [b, max_vio], k_out [b]; k_out[i] = -1 marks a pair whose query or old keyframe is
+ * not (or no longer) resident on any rank - the other pairs of the batch are still matched. */
 dv_status dv_batch_match(dv_engine* e, int32_t b, const int64_t* query_ids, const int64_t* old_ids, int32_t* matches,
                          float* mscores, int32_t* k_out);
+/* Which of a stored keyframe's points form the QUERY side of a match (the old side is always its full point set). */
+#define DV_PART_WINDOW 0   /* the caller-supplied window / VIO points + SP_RE descriptors (keyframe.cpp:605-618) */
+#define DV_PART_SP 1       /* its SuperPoint keypoints + descriptors (BASELINE config "SP+LG 512-kpt pair match") */
+#define DV_PART_ALL 2      /* SP ++ window points */
+/* dv_batch_match with a selectable query part and old part; out_cap = row capacity per pair of matches / mscores
+ * (>= the largest query-side point count).  dv_batch_match == (DV_PART_WINDOW, DV_PART_ALL, max_vio). */
+dv_status dv_batch_match_ex(dv_engine* e, int32_t b, const int64_t* query_ids, const int64_t* old_ids,
+                            int32_t query_part, int32_t old_part, int32_t out_cap, int32_t* matches, float* mscores,
+                            int32_t* k_out);
+/* MixVPR only for the b uploaded frames (BASELINE config "MixVPR + kNN"): MixVPR::mix_extractor, deep_net.cpp:1254-1323,
+ * batched; follow with dv_batch_commit / dv_batch_search.  No local features are extracted or stored. */
+dv_status dv_batch_describe_global(dv_engine* e, int32_t b);
 /* Read one stored keyframe back (tests / persistence): kpts [n,2] f32, desc [n,256], n_sp = SuperPoint share. */
 dv_status dv_store_read(dv_engine* e, int64_t frame_id, float* kpts_xy, float* desc, int32_t* n_total, int32_t* n_sp);
 /* Restores a keyframe's local features into the store (the inverse of dv_store_read): rows [0, n_sp) are its SuperPoint
@@ -144,6 +159,14 @@ dv_status dv_store_read(dv_engine* e, int64_t frame_id, float* kpts_xy, float* d
  * restores the deep features it saved (:1042-1069), so a reloaded map cannot close loops there. */
 dv_status dv_store_put(dv_engine* e, int64_t frame_id, const float* kpts_xy, const float* desc, int32_t n_total,
                        int32_t n_sp);
+/* Where does keyframe frame_id live?  owner_rank = -1 if no rank holds it (never stored, or its ring slot was reused).
+ * The store is a ring of store_capacity keyframes per rank (about (max_kpts + max_vio) * 1032 bytes each): size it to the
+ * number of keyframes that may still be loop candidates - the whole session at 0.7 MB per EuRoC keyframe fits HBM. */
+dv_status dv_store_lookup(dv_engine* e, int64_t frame_id, int32_t* owner_rank, int32_t* n_total, int32_t* n_sp);
+dv_status dv_store_lookup_many(dv_engine* e, int32_t n, const int64_t* frame_ids, int32_t* owner_rank);
+/* Collective (all ranks): re-publishes every rank's slot directory, e.g. after dv_store_put / a session reload, so
+ * peers can match against keyframes that never went through a round all-gather.  No-op for world_size == 1. */
+dv_status dv_store_sync(dv_engine* e);
 /* Results of the last dv_batch_extract for frame slot i (host copies). */
 dv_status dv_batch_read_global(dv_engine* e, int32_t i, float* des512);
 
@@ -166,6 +189,8 @@ dv_status dv_stats_enable(dv_engine* e, int32_t on);   /* stage timing costs eve
 /* Event pair around every launch of the dominant kernel (conv1b implicit GEMM, 43 % of SuperPoint's MACs): its
  * accumulated device time and launch count inside the caller's timed region -> roofline.achieved in bench.py. */
 dv_status dv_probe_enable(dv_engine* e, int32_t on);
+/* which kernel the probe brackets: 0 = conv1a+conv1b implicit GEMM (default), 1 = kNN bank scan (HBM-bound). */
+dv_status dv_probe_select(dv_engine* e, int32_t which);
 dv_status dv_probe_read(dv_engine* e, double* ms, int64_t* launches, int32_t reset);
 
 /* ------------------------------------------------------------------------------------------------

@@ -144,3 +144,80 @@ def test_session_save_load_roundtrip(eng, weights_file, tmp_path):
         assert np.array_equal(m0[0], m1[0]) and np.array_equal(m0[1], m1[1])
     finally:
         e2.close()
+
+
+def test_store_ring_eviction_is_per_pair_status(weights_file):
+    """The feature store is a ring: a keyframe whose slot was reused is reported as k_out = -1 for ITS pair only, the
+    other pairs of the batch are still matched (the whole batch used to fail with DV_ERR_INVALID)."""
+    from d_vins_b200 import capi
+    from oracle import synth
+    H, W, b = 160, 224, 2
+    e = capi.Engine(height=H, width=W, weights_path=weights_file, max_batch=b, max_vio=64, store_capacity=4,
+                    bank_capacity=64)
+    try:
+        st = synth.Stream(H, W, period=12, margin=48)
+        vio = np.zeros((b, 64, 2), np.float32); nv = np.full((b,), 40, np.int32)
+        vio[:, :40] = synth.vio_points(40, H, W, 5, min_dist=12)
+        for r in range(3):                                   # 6 keyframes through a 4-slot ring: 0 and 1 are evicted
+            ids = np.arange(b, dtype=np.int64) + r * b
+            e.batch_upload(np.stack([st.frame(int(t)) for t in ids]))
+            e.batch_extract(vio, nv, ids)
+            e.batch_commit(b)
+        assert e.store_lookup(0)[0] == -1 and e.store_lookup(1)[0] == -1
+        assert e.store_lookup(2)[0] == 0 and e.store_lookup(5) == (0, e.store_lookup(5)[1], e.store_lookup(5)[2])
+        assert list(e.store_lookup_many([0, 3, 99, 5])) == [-1, 0, -1, 0]
+        res = e.batch_match(np.array([4, 5], np.int64), np.array([0, 3], np.int64))
+        assert list(e.last_match_status >= 0) == [False, True]
+        assert len(res[0][0]) == 0 and e.last_match_status[0] == -1
+        ref = e.batch_match(np.array([5], np.int64), np.array([3], np.int64))[0]
+        assert np.array_equal(res[1][0], ref[0]) and np.array_equal(res[1][1], ref[1])
+        with pytest.raises(capi.DvError):
+            e.store_read(0)
+    finally:
+        e.close()
+
+
+def test_engine_window_rule_and_global_only_round(eng):
+    """dv_batch_search(nb_limit = NULL) applies keyframe.cpp:274-282 with cfg.exclude_recent itself;
+    dv_batch_describe_global runs MixVPR alone and yields the same descriptors as the full extraction."""
+    from oracle import knn, synth
+    st = synth.Stream(480, 752, period=12, margin=64)
+    b = 4
+    frames = np.stack([st.frame(t) for t in range(40, 40 + b)])
+    vio = np.zeros((b, 160, 2), np.float32); nv = np.zeros((b,), np.int32)
+    bank, _ = synth.make_bank(300, seed=11)
+    eng.bank_import(bank)
+    eng.batch_upload(frames); eng.batch_extract(vio, nv, np.arange(200, 200 + b, dtype=np.int64))
+    g_full = [eng.batch_read_global(i) for i in range(b)]
+    first = eng.batch_commit(b)
+    assert first == 300
+    D0, I0 = eng.batch_search([knn.nb_limit(300 + i) for i in range(b)])
+    D1, I1 = eng.batch_search(None, b)
+    assert np.array_equal(I0, I1) and np.array_equal(D0, D1)
+    eng.bank_import(bank)
+    eng.batch_upload(frames); eng.batch_describe_global(b)
+    assert all(np.array_equal(eng.batch_read_global(i), g_full[i]) for i in range(b))
+    assert eng.batch_commit(b) == 300
+    D2, I2 = eng.batch_search(None, b)
+    assert np.array_equal(I0, I2) and np.array_equal(D0, D2)
+
+
+def test_match_sp_part_equals_host_vector_match(eng):
+    """BASELINE config 2 path: dv_batch_match_ex(DV_PART_SP, DV_PART_SP) on stored keyframes == dv_lg_match on the same
+    SuperPoint keypoints / descriptors passed as host vectors."""
+    from oracle import synth
+    a, bimg = synth.make_pair(shift=(8, 16))
+    vio = np.zeros((2, 160, 2), np.float32); nv = np.zeros((2,), np.int32)
+    eng.batch_upload(np.stack([a, bimg])); eng.batch_extract(vio, nv, np.array([900, 901], np.int64))
+    m, s = eng.batch_match_sp(np.array([900], np.int64), np.array([901], np.int64))[0]
+    ka, da, na = eng.store_read(900); kb, db, nb = eng.store_read(901)
+    assert na == len(ka) == 512 and nb == len(kb) == 512
+    m2, s2 = eng.lg_match(ka, kb, da, db, 480, 752, 480, 752)
+    assert len(m) > 20 and np.array_equal(m, m2) and np.array_equal(s, s2)
+
+
+def test_config_validation(weights_file):
+    from d_vins_b200 import capi
+    for kw in (dict(max_vio=600), dict(max_kpts=1024, max_vio=64), dict(max_batch=8, store_capacity=4)):
+        with pytest.raises(capi.DvError):
+            capi.Engine(height=160, width=224, weights_path=weights_file, **kw)
