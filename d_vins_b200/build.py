@@ -90,13 +90,31 @@ def build_shim_demo() -> str:
     exe = os.path.join(BUILD, "shim_demo")
     srcs = [os.path.join(CSRC, "shim", "deep_net_shim.cpp"),
             os.path.join(os.path.dirname(HERE), "tests", "cpp", "shim_demo.cpp")]
-    if not os.path.exists(exe) or any(os.path.getmtime(x) > os.path.getmtime(exe) for x in srcs + [lib]):
+    deps = srcs + [lib, os.path.join(CSRC, "shim", "deep_net_shim.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(x) > os.path.getmtime(exe) for x in deps):
         cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe] + srcs + [
             "-L" + HERE, "-ldvins_b200", "-Wl,-rpath," + HERE]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("shim build failed")
+    return exe
+
+
+def build_stream_demo() -> str:
+    """g++ build of the ROS-free keyframe stream driver (csrc/shim/loop_closure.cpp) + tests/cpp/stream_demo.cpp."""
+    lib = LIB if os.path.exists(LIB) else build()
+    os.makedirs(BUILD, exist_ok=True)
+    exe = os.path.join(BUILD, "stream_demo")
+    srcs = [os.path.join(CSRC, "shim", "loop_closure.cpp"),
+            os.path.join(os.path.dirname(HERE), "tests", "cpp", "stream_demo.cpp")]
+    deps = srcs + [lib, os.path.join(CSRC, "shim", "loop_closure.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(x) > os.path.getmtime(exe) for x in deps):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-o", exe] + srcs + ["-L" + HERE, "-ldvins_b200", "-Wl,-rpath," + HERE]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("stream demo build failed")
     return exe
 
 

@@ -29,6 +29,19 @@ class DvConfig(C.Structure):
                 ("rank", C.c_int32), ("weights_path", C.c_char_p)]
 
 
+class DvLoopParams(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("min_loop_num", C.c_int32), ("ransac_iters", C.c_int32),
+                ("min_frame_index", C.c_int32), ("pnp_inflation", C.c_double), ("max_theta_diff", C.c_double),
+                ("max_pose_diff", C.c_double), ("loop_top_thres", C.c_double), ("loop_back_thres", C.c_double),
+                ("qic", C.c_double * 9), ("tic", C.c_double * 3), ("seed", C.c_uint64)]
+
+
+class DvLoopResult(C.Structure):
+    _fields_ = [("has_loop", C.c_int32), ("n_inliers", C.c_int32), ("pnp_t_old", C.c_double * 3),
+                ("pnp_r_old", C.c_double * 9), ("relative_t", C.c_double * 3), ("relative_q", C.c_double * 4),
+                ("relative_yaw", C.c_double)]
+
+
 class DvError(RuntimeError):
     def __init__(self, status, msg):
         super().__init__("%s: %s" % (STATUS.get(status, status), msg))
@@ -70,6 +83,26 @@ def default_config(**kw) -> DvConfig:
             v = os.fsencode(v)
         setattr(cfg, k, v)
     return cfg
+
+
+def loop_params(qic=None, tic=None, **kw) -> DvLoopParams:
+    p = DvLoopParams()
+    _lib.dv_loop_params_default(C.byref(p))
+    if qic is not None:
+        p.qic = (C.c_double * 9)(*np.asarray(qic, np.float64).reshape(9))
+    if tic is not None:
+        p.tic = (C.c_double * 3)(*np.asarray(tic, np.float64).reshape(3))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def detect_loop(params: DvLoopParams, top_sim, top_sim_index, frame_index) -> int:
+    """PoseGraph::detectLoop (pose_graph.cpp:451-509) on one keyframe's kNN result."""
+    d = np.ascontiguousarray(top_sim, np.float32); i = np.ascontiguousarray(top_sim_index, np.int64)
+    _lib.dv_detect_loop.restype = C.c_int64
+    return int(_lib.dv_detect_loop(C.byref(params), _ptr(d, C.c_float), _ptr(i, C.c_int64), int(d.shape[0]),
+                                   C.c_int64(int(frame_index))))
 
 
 def comm_unique_id() -> bytes:
@@ -232,6 +265,29 @@ class Engine:
         out = np.full((ids.shape[0],), -1, np.int32)
         _chk(_lib.dv_store_lookup_many(self._h, int(ids.shape[0]), _ptr(ids, C.c_int64), _ptr(out, C.c_int32)))
         return out
+
+    def verify_loop(self, pts3d, pts2d_norm, vio_R, vio_T, params: DvLoopParams):
+        """Batched KeyFrame::PnPRANSAC + findConnection acceptance.  pts3d: list of [n_i,3], pts2d_norm: list of
+        [n_i,2], vio_R [b,3,3], vio_T [b,3].  -> list of dicts (status, has_loop, n_inliers, poses)."""
+        b = len(pts3d)
+        n = np.array([len(x) for x in pts3d], np.int32)
+        cap = max(1, int(n.max()))
+        X = np.zeros((b, cap, 3), np.float64); U = np.zeros((b, cap, 2), np.float64)
+        for i in range(b):
+            X[i, :n[i]] = pts3d[i]; U[i, :n[i]] = pts2d_norm[i]
+        R = np.ascontiguousarray(vio_R, np.float64).reshape(b, 9); T = np.ascontiguousarray(vio_T, np.float64).reshape(b, 3)
+        st = np.zeros((b, cap), np.uint8)
+        out = (DvLoopResult * b)()
+        _chk(_lib.dv_verify_loop(self._h, b, _ptr(n, C.c_int32), cap, _ptr(X, C.c_double), _ptr(U, C.c_double),
+                                 _ptr(R, C.c_double), _ptr(T, C.c_double), C.byref(params), _ptr(st, C.c_uint8), out))
+        res = []
+        for i in range(b):
+            o = out[i]
+            res.append(dict(has_loop=bool(o.has_loop), n_inliers=int(o.n_inliers), status=st[i, :n[i]].copy(),
+                            pnp_T_old=np.array(o.pnp_t_old), pnp_R_old=np.array(o.pnp_r_old).reshape(3, 3),
+                            relative_t=np.array(o.relative_t), relative_q=np.array(o.relative_q),
+                            relative_yaw=float(o.relative_yaw)))
+        return res
 
     def store_lookup(self, frame_id):
         """-> (owner_rank or -1, n_total, n_sp)"""

@@ -3,6 +3,8 @@
 // 128-bit coalesced loads; one warp per bank row, the queries live in registers, warp-shuffle dot products,
 // per-block partial top-k in shared memory, then a single-block merge.  Tie rule: lowest index first.
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -26,7 +28,9 @@ struct Bank {
   float* outD = nullptr;       // [B, K]
   long long* outI = nullptr;
   long long* d_nb = nullptr;   // [B]
+  unsigned int* d_ticket = nullptr;   // [ceil(B / KNN_QB)] "blocks finished" counters of the fused merge (self-resetting)
   int nblocks_cap = 0;
+  bool fused = true;           // DV_KNN_FUSED=0: two launches + limit upload + result copies (A/B)
   float* h_D = nullptr; long long* h_I = nullptr; long long* h_nb = nullptr; float* h_q = nullptr;   // pinned
 };
 
@@ -52,12 +56,21 @@ __device__ __forceinline__ void topk_insert(float (&D)[K], long long (&I)[K], fl
 // registers; the 8 query vectors sit in shared memory.  The 32 partial dot products (4 rows x 8 queries) of a lane
 // are reduced across the warp with a 31-shuffle butterfly that leaves lane L holding the total of pair L, so lane L
 // owns the candidate list of query (L & 7) for row slot (L >> 3).
-template <int K>
+// Search windows by value (kernel arguments) for up to 64 queries: no host->device copy before the launch.
+struct KnnLimits { long long v[64]; };
+
+// FUSED == true: the block that finishes last for its query group (ticket counter) merges the per-block candidate
+// lists and writes the final top-k - to device memory or straight into mapped pinned host memory - so a search is ONE
+// launch with no limit upload and no result copy (r01: 41 us per 10k-row search, 37 us of it fixed cost).
+template <int K, bool FUSED>
 __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_scan(const float* __restrict__ bank,
                                                             const float* __restrict__ q,
-                                                            const long long* __restrict__ nb_limit, int nq,
+                                                            const long long* __restrict__ nb_limit_dev,
+                                                            const KnnLimits lim_args, int nq,
                                                             float* __restrict__ partD, long long* __restrict__ partI,
-                                                            int nblocks) {
+                                                            int nblocks, unsigned int* __restrict__ ticket,
+                                                            float* __restrict__ outD, long long* __restrict__ outI) {
+  const long long* __restrict__ nb_limit = nb_limit_dev ? nb_limit_dev : lim_args.v;
   __shared__ __align__(16) float sq[KNN_QB][512];
   __shared__ float sD[KNN_QB][KNN_WARPS * 4][K];
   __shared__ long long sI[KNN_QB][KNN_WARPS * 4][K];
@@ -142,6 +155,42 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_scan(const float* __rest
       partI[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bI[t];
     }
   }
+  if (!FUSED) return;
+  // ---- fused merge: last block of this query group
+  __shared__ unsigned int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&ticket[blockIdx.y], 1u) == (unsigned)gridDim.x - 1u) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (warp < nqb) {                                  // one warp per query of the group
+    const int j = warp;
+    float mD[K]; long long mI[K];
+#pragma unroll
+    for (int t = 0; t < K; ++t) { mD[t] = -INFINITY; mI[t] = -1; }
+    for (int b = lane; b < nblocks; b += 32)
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const long long i = __ldcg(&partI[((int64_t)(q0 + j) * nblocks + b) * K + t]);
+        if (i >= 0) topk_insert<K>(mD, mI, __ldcg(&partD[((int64_t)(q0 + j) * nblocks + b) * K + t]), i);
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float oD[K]; long long oI[K];
+#pragma unroll
+      for (int t = 0; t < K; ++t) { oD[t] = __shfl_xor_sync(0xffffffffu, mD[t], o); oI[t] = __shfl_xor_sync(0xffffffffu, mI[t], o); }
+#pragma unroll
+      for (int t = 0; t < K; ++t)
+        if (oI[t] >= 0) topk_insert<K>(mD, mI, oD[t], oI[t]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int t = 0; t < K; ++t) { outD[(int64_t)(q0 + j) * K + t] = mD[t]; outI[(int64_t)(q0 + j) * K + t] = mI[t]; }
+      __threadfence_system();                        // the outputs may live in mapped host memory
+    }
+  }
+  if (threadIdx.x == 0) ticket[blockIdx.y] = 0u;     // ready for the next launch
 }
 
 // one block per query: merge nblocks partial lists (strided gather, then a shared-memory tree)
@@ -178,13 +227,18 @@ __global__ void __launch_bounds__(256) k_knn_merge(const float* __restrict__ par
 }
 
 template <int K>
-static void knn_launch(Engine* e, const float* rows, const float* q, const long long* d_nb, int nq, int nblocks, float* partD,
-                       long long* partI, float* outD, long long* outI, cudaStream_t st) {
-  {
-    ProbeScope pr(e, 1);   // roofline probe of the HBM-bound scan (bench.py --config mix_knn_10k)
-    k_knn_scan<K><<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, st>>>(rows, q, d_nb, nq, partD, partI, nblocks);
+static void knn_launch(Engine* e, const float* rows, const float* q, const long long* d_nb, const KnnLimits& lim, int nq,
+                       int nblocks, float* partD, long long* partI, unsigned int* ticket, float* outD, long long* outI,
+                       bool fused, cudaStream_t st) {
+  ProbeScope pr(e, 1);   // roofline probe of the HBM-bound scan (bench.py --config mix_knn_10k)
+  if (fused) {
+    k_knn_scan<K, true><<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, st>>>(rows, q, d_nb, lim, nq, partD, partI,
+                                                                                 nblocks, ticket, outD, outI);
+  } else {
+    k_knn_scan<K, false><<<dim3(nblocks, cdiv(nq, KNN_QB)), KNN_WARPS * 32, 0, st>>>(rows, q, d_nb, lim, nq, partD, partI,
+                                                                                  nblocks, ticket, outD, outI);
+    k_knn_merge<K><<<nq, 256, 0, st>>>(partD, partI, nblocks, outD, outI);
   }
-  k_knn_merge<K><<<nq, 256, 0, st>>>(partD, partI, nblocks, outD, outI);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -201,6 +255,8 @@ int bank_init(Engine* e) {
   DV_TRY(e->alloc(&b->outD, (size_t)B * K));
   DV_TRY(e->alloc(&b->outI, (size_t)B * K));
   DV_TRY(e->alloc(&b->d_nb, (size_t)B));
+  DV_TRY(e->alloc(&b->d_ticket, (size_t)cdiv(B, KNN_QB) + 1));
+  { const char* env = getenv("DV_KNN_FUSED"); b->fused = !(env && env[0] == '0'); }
   DV_TRY(e->alloc_pinned(&b->h_D, (size_t)B * K));
   DV_TRY(e->alloc_pinned(&b->h_I, (size_t)B * K));
   DV_TRY(e->alloc_pinned(&b->h_nb, (size_t)B));
@@ -213,15 +269,17 @@ float* bank_rows(Engine* e) { return e->bank->rows; }
 float* bank_query_buf(Engine* e) { return e->bank->q; }
 int64_t& bank_size_ref(Engine* e) { return e->bank->size; }
 
-// queries already in bank->q (device); nb_limit host array [nq]
-int bank_search_device(Engine* e, int nq, const int64_t* nb_limit, int k, float* D_host, int64_t* I_host) {
+// queries at `d_q` (device memory, or mapped pinned host memory); nb_limit host array [nq]
+static int bank_search_impl(Engine* e, const float* d_q, int nq, const int64_t* nb_limit, int k, float* D_host, int64_t* I_host) {
   Bank* b = e->bank;
   if (nq <= 0) return DV_OK;
   if (k < 1 || k > KNN_MAXK) { set_error("knn: k out of range"); return DV_ERR_INVALID; }
+  KnnLimits lim;
   long long maxlim = 0;
   for (int i = 0; i < nq; ++i) {
     long long l = std::max<long long>(0, std::min<long long>(nb_limit[i], b->size));
     b->h_nb[i] = l;
+    if (i < 64) lim.v[i] = l;
     maxlim = std::max(maxlim, l);
   }
   StageScope sc(e, ST_KNN);
@@ -229,27 +287,37 @@ int bank_search_device(Engine* e, int nq, const int64_t* nb_limit, int k, float*
     for (int i = 0; i < nq * k; ++i) { D_host[i] = -INFINITY; I_host[i] = -1; }
     return DV_OK;
   }
-  DV_CUDA_OK(cudaMemcpyAsync(b->d_nb, b->h_nb, sizeof(long long) * nq, cudaMemcpyHostToDevice, e->st));
-  int dev_sms = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev); }
+  // fused path: limits by value, merge in the scan's last block, results written straight into pinned host memory
+  const bool fused = b->fused && nq <= 64;
+  const long long* d_nb = nullptr;
+  if (!fused) {
+    DV_CUDA_OK(cudaMemcpyAsync(b->d_nb, b->h_nb, sizeof(long long) * nq, cudaMemcpyHostToDevice, e->st));
+    d_nb = b->d_nb;
+  }
+  float* oD = fused ? b->h_D : b->outD;
+  long long* oI = fused ? b->h_I : b->outI;
+  static int dev_sms = 0;
+  if (!dev_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int nblocks = (int)std::min<int64_t>(cdiv64(maxlim, KNN_ROWS_PER_BLOCK), (int64_t)dev_sms * 2);   // 128 registers x 256 threads: two resident blocks per SM
   switch (k) {
-    case 1: knn_launch<1>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 2: knn_launch<2>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 3: knn_launch<3>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 4: knn_launch<4>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 5: knn_launch<5>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 6: knn_launch<6>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    case 7: knn_launch<7>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
-    default: knn_launch<8>(e, b->rows, b->q, b->d_nb, nq, nblocks, b->partD, b->partI, b->outD, b->outI, e->st); break;
+#define DV_KNN_CASE(KK) case KK: knn_launch<KK>(e, b->rows, d_q, d_nb, lim, nq, nblocks, b->partD, b->partI, b->d_ticket, oD, oI, fused, e->st); break;
+    DV_KNN_CASE(1) DV_KNN_CASE(2) DV_KNN_CASE(3) DV_KNN_CASE(4) DV_KNN_CASE(5) DV_KNN_CASE(6) DV_KNN_CASE(7)
+    default: knn_launch<8>(e, b->rows, d_q, d_nb, lim, nq, nblocks, b->partD, b->partI, b->d_ticket, oD, oI, fused, e->st); break;
+#undef DV_KNN_CASE
   }
   DV_CUDA_OK(cudaGetLastError());
-  DV_LAUNCHED(e, 2);
-  DV_CUDA_OK(cudaMemcpyAsync(b->h_D, b->outD, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, e->st));
-  DV_CUDA_OK(cudaMemcpyAsync(b->h_I, b->outI, sizeof(long long) * nq * k, cudaMemcpyDeviceToHost, e->st));
+  DV_LAUNCHED(e, fused ? 1 : 2);
+  if (!fused) {
+    DV_CUDA_OK(cudaMemcpyAsync(b->h_D, b->outD, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(b->h_I, b->outI, sizeof(long long) * nq * k, cudaMemcpyDeviceToHost, e->st));
+  }
   DV_CUDA_OK(cudaStreamSynchronize(e->st));
   for (int i = 0; i < nq * k; ++i) { D_host[i] = b->h_D[i]; I_host[i] = (int64_t)b->h_I[i]; }
   return DV_OK;
+}
+
+int bank_search_device(Engine* e, int nq, const int64_t* nb_limit, int k, float* D_host, int64_t* I_host) {
+  return bank_search_impl(e, e->bank->q, nq, nb_limit, k, D_host, I_host);
 }
 
 }  // namespace dv
@@ -282,6 +350,11 @@ dv_status dv_bank_search(dv_engine* h, const float* q512, int64_t nb_limit, int3
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
   if (!q512 || !D || !I || k < 1 || k > KNN_MAXK) { set_error("dv_bank_search: bad argument"); return DV_ERR_INVALID; }
+  if (e->bank->fused) {
+    // the single query is read by the kernel straight from mapped pinned host memory (2 KB over PCIe): no H2D copy
+    memcpy(e->bank->h_q, q512, 512 * sizeof(float));
+    return (dv_status)bank_search_impl(e, e->bank->h_q, 1, &nb_limit, k, D, I);
+  }
   DV_CUDA_OK(cudaMemcpyAsync(e->bank->q, q512, 512 * sizeof(float), cudaMemcpyHostToDevice, e->st));
   return (dv_status)bank_search_device(e, 1, &nb_limit, k, D, I);
 }

@@ -10,6 +10,7 @@
 //     uploaded once and the SuperPoint encoder runs once per keyframe;
 //   * the kNN lives behind MixVPR::sort_in_bank(index) instead of a per-query faiss rebuild (keyframe.cpp:262-346).
 #pragma once
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -58,13 +59,21 @@ class MixVPR {
   // keyframe.cpp:262-346 (sort_vec_faiss): appends nothing; searches bank rows [0, index-50] (or [0,index] if
   // index < 50) for the current mix_des and fills top_sim_index / top_sim.
   virtual void sort_in_bank(int index) = 0;
-  virtual void sort_in_faiss(float* db, float* xq, int n) = 0;          // deep_net.h:123 (imports db, then searches)
+  // deep_net.h:123 declares (db, xq, n) but the implementation (deep_net.cpp:1325) and its only caller (:1399) pass
+  // the QUERY first: sort_in_faiss(xq, db, nb).  Behaviour follows the implementation: import db [nb,512], search xq,
+  // append the top-3 to top_sim_index / top_sim and to sim_map[call counter].
+  virtual void sort_in_faiss(float* xq, float* db, int nb) = 0;
+  // deep_net.h:122 / deep_net.cpp:1386-1428: run every image of a folder through mix_extractor + sort_in_faiss (the
+  // newest 15 excluded) filling descriptors_database / sim_map / top_sim.  The reference then cv::imshow()s the top-3;
+  // here the results stay in the members.  Without OpenCV the folder is scanned for binary PGM (P5) files.
+  virtual void test_in_dataset(const std::string filepath) = 0;
   virtual long append_to_bank() = 0;                                    // keyframe.cpp:353
 
   std::vector<float> descriptors_database;   // kept for source compatibility; the live bank is device-resident
   std::vector<float> mix_des;                // 512
   std::vector<int> top_sim_index;
   std::vector<float> top_sim;
+  std::map<int, vector<int>> sim_map;        // deep_net.h:134
 };
 shared_ptr<MixVPR> creat_mix(const std::string& weights_path, const int& engine_type, int gpuid = 0, int height = 480,
                              int width = 752);
@@ -81,6 +90,9 @@ class Estimator {
   virtual void lg_matcher(std::vector<dv::Pt>& lg_in_kpts0, std::vector<dv::Pt>& lg_in_kpts1,
                           std::vector<float>& lg_in_desc0, std::vector<float>& lg_in_desc1, const int& height_0,
                           const int& width_0, const int& height_1, const int& width_1) = 0;   // deep_net.h:146-151
+  // deep_net.h:153 / deep_net.cpp:1003-1133 (legacy, no caller in the reference): LightGlue on the keypoints the last
+  // sp_extractor(img) produced, used for BOTH sides (the SuperPoint output tensors are bound as kpts0 and kpts1).
+  virtual void lg_matcher() = 0;
 #ifdef DV_SHIM_WITH_OPENCV
   void sp_extractor(const cv::Mat& img) { sp_extractor(dv::as_image(img)); }
   void sp_extractor(const cv::Mat& img, vector<cv::Point2f>& k) { sp_extractor(dv::as_image(img), k); }
@@ -100,6 +112,11 @@ class Estimator {
   vector<float> lg_scores;
   vector<dv::Pt> lg_mkpts0;
   vector<dv::Pt> lg_mkpts1;
+#ifdef DV_SHIM_WITH_OPENCV
+  cv::Mat image;                             // deep_net.h:169
+#else
+  dv::Image image;                           // deep_net.h:169 (non-owning view of the last frame)
+#endif
 };
 
 // engine_type 0: SP, 1: SP_RE, 2: LG (deep_net.cpp:1198-1203) - all three views share one dv_engine.

@@ -170,6 +170,44 @@ dv_status dv_store_sync(dv_engine* e);
 /* Results of the last dv_batch_extract for frame slot i (host copies). */
 dv_status dv_batch_read_global(dv_engine* e, int32_t i, float* des512);
 
+/* ------------------------------------------------------------------------------------------------
+ * Loop decision + geometric verification (the step right after LightGlue).
+ * ---------------------------------------------------------------------------------------------- */
+/* Replaces the YAML keys read in pose_graph_node.cpp:480-486 and the constants of keyframe.cpp:835 / pose_graph.cpp:470. */
+typedef struct dv_loop_params {
+  int32_t struct_size;         /* = sizeof(dv_loop_params)                                        */
+  int32_t min_loop_num;        /* MIN_LOOP_NUM 18                                                 */
+  int32_t ransac_iters;        /* 200 hypotheses (keyframe.cpp:835); all are evaluated, in parallel */
+  int32_t min_frame_index;     /* 50: detectLoop only fires for frame_index > 50 (pose_graph.cpp:470) */
+  double pnp_inflation;        /* PNP_INFLATION 3.5: reprojection threshold = pnp_inflation / 460  */
+  double max_theta_diff;       /* MAX_THETA_DIFF 40 (degrees)                                     */
+  double max_pose_diff;        /* MAX_POSE_DIFF 25 (metres)                                       */
+  double loop_top_thres;       /* 0.45                                                            */
+  double loop_back_thres;      /* 0.40                                                            */
+  double qic[9], tic[3];       /* camera -> body extrinsics (row-major rotation), keyframe.cpp:817 */
+  uint64_t seed;               /* hypothesis sampling stream (counter-based, reproducible)        */
+} dv_loop_params;
+typedef struct dv_loop_result {
+  int32_t has_loop;            /* KeyFrame::findConnection's return value                          */
+  int32_t n_inliers;           /* matches surviving PnP-RANSAC                                    */
+  double pnp_t_old[3], pnp_r_old[9];   /* PnP_T_old / PnP_R_old (body pose of the old keyframe, row-major) */
+  double relative_t[3], relative_q[4], relative_yaw;   /* loop_info: t, q (w,x,y,z), yaw in degrees        */
+} dv_loop_result;
+void dv_loop_params_default(dv_loop_params* p);
+/* PoseGraph::detectLoop  pose_graph.cpp:451-509: top_sim / top_sim_index = the keyframe's kNN result (dv_bank_search);
+ * returns the loop candidate's keyframe index (the SMALLEST qualifying one) or -1.  Pure host arithmetic. */
+int64_t dv_detect_loop(const dv_loop_params* p, const float* top_sim, const int64_t* top_sim_index, int32_t k,
+                       int64_t frame_index);
+/* KeyFrame::PnPRANSAC  keyframe.cpp:805-868 + the acceptance test of findConnection :1094-1183, for b pairs at once.
+ * Per pair i: n_pts[i] correspondences - pts3d [b,cap,3] the CURRENT keyframe's matched 3-D points (world frame),
+ * pts2d_norm [b,cap,2] the matched OLD keypoints in normalised image coordinates - and the current keyframe's VIO pose
+ * vio_R [b,9] (row-major), vio_T [b,3] (the extrinsic guess).  status [b,cap] receives the inlier mask (the reference's
+ * `status` vector), out [b] the poses and the loop decision.  Pairs with n_pts <= min_loop_num are skipped like the
+ * reference does (has_loop = 0). */
+dv_status dv_verify_loop(dv_engine* e, int32_t b, const int32_t* n_pts, int32_t cap, const double* pts3d,
+                         const double* pts2d_norm, const double* vio_R, const double* vio_T, const dv_loop_params* p,
+                         uint8_t* status, dv_loop_result* out);
+
 /* Multi-GPU plumbing: the host passes the 128-byte ncclUniqueId it broadcast over its own channel
  * (torch.distributed in bench.py).  rank/world_size come from dv_config. */
 dv_status dv_comm_unique_id(void* id128);

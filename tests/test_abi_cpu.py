@@ -83,3 +83,26 @@ def test_cpp_shim_compiles_against_the_header(tmp_path):
     assert r.returncode == 0, r.stderr
     exe = build.build_shim_demo()
     assert os.path.exists(exe) and os.path.exists(lib)
+
+
+def test_shim_opencv_overloads_and_stream_driver_compile(tmp_path):
+    """The cv::Mat / cv::Point2f overloads (DV_SHIM_WITH_OPENCV) compile against a minimal stand-in for
+    <opencv2/core.hpp> (tests/cpp/opencv_stub; no OpenCV C++ headers in this image), and the ROS-free stream driver
+    (csrc/shim/loop_closure.cpp) builds and links against the C-ABI library with g++ alone."""
+    import subprocess
+    from d_vins_b200 import build
+    src = tmp_path / "cvuse.cpp"
+    src.write_text('''
+#include "deep_net_shim.h"
+int use(Estimator_net::Estimator* e, MixVPR_net::MixVPR* m, const cv::Mat& img, std::vector<cv::Point2f>& pts) {
+  e->sp_extractor(img); e->sp_extractor(img, pts); e->lg_matcher(); m->mix_extractor(img); m->test_in_dataset("/tmp");
+  return (int)e->sp_kpts.size() + (int)m->sim_map.size() + e->image.rows;
+}
+''')
+    inc = ["-I", os.path.join(ROOT, "tests", "cpp", "opencv_stub"), "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "d_vins_b200", "csrc", "shim")]
+    for unit in (str(src), os.path.join(ROOT, "d_vins_b200", "csrc", "shim", "deep_net_shim.cpp")):
+        r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-DDV_SHIM_WITH_OPENCV", "-c", unit, "-o",
+                            str(tmp_path / "o.o")] + inc, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    assert os.path.exists(build.build_stream_demo())

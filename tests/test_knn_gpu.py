@@ -54,3 +54,32 @@ def test_append_and_window(eng):
         Do, Io = knn.knn_ip(np.stack(rows), d, nb)
         assert np.array_equal(I, Io)
     assert np.allclose(eng.bank_export(), np.stack(rows))
+
+
+def test_fused_single_launch_equals_two_launch_path(monkeypatch):
+    """Default search = ONE launch (limits as kernel arguments, merge in the scan's last block, results written into
+    mapped pinned host memory).  DV_KNN_FUSED=0 selects the r01 path (limit upload + scan + merge + two result copies);
+    both must return bit-identical (D, I) - repeatedly (the ticket counters reset themselves)."""
+    from d_vins_b200 import capi
+    from oracle import knn, synth
+    bank, q = synth.make_bank(20000, seed=7)
+    rng = np.random.default_rng(3)
+    qs = [q] + [bank[i] + 0.05 * rng.standard_normal(512).astype(np.float32) for i in (5, 777, 19999)]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DV_KNN_FUSED", mode)
+        e = capi.Engine(height=64, width=64, bank_capacity=20000)
+        try:
+            e.bank_import(bank)
+            out = []
+            for rep in range(3):
+                for x in qs:
+                    for nb in (20000, 9951, 130, 3, 1):
+                        out.append(e.bank_search(x, nb))
+            res[mode] = out
+        finally:
+            e.close()
+    for (D1, I1), (D0, I0) in zip(res["1"], res["0"]):
+        assert np.array_equal(I1, I0) and np.array_equal(D1, D0)
+    Do, Io = knn.knn_ip(bank, q, 20000)
+    assert np.array_equal(res["1"][0][1], Io)
