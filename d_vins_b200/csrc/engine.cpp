@@ -3,6 +3,7 @@
 #include "engine.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -108,6 +109,7 @@ dv_status dv_create(const dv_config* cfg, dv_engine** out) {
   e->cfg = *cfg;
   if (cfg->weights_path) { e->weights_path = cfg->weights_path; e->cfg.weights_path = e->weights_path.c_str(); }
   e->B = cfg->max_batch; e->H = cfg->height; e->W = cfg->width;
+  { const char* env = getenv("DV_GRAPHS"); e->graphs_on = !(env && env[0] == '0'); }
   e->h8 = e->H / 8; e->w8 = e->W / 8;
   auto fail = [&](int rc) { dv_destroy(reinterpret_cast<dv_engine*>(e)); return (dv_status)rc; };
   if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); return fail(DV_ERR_CUDA); }

@@ -89,6 +89,9 @@ struct Engine {
   Store* store = nullptr;
   Comm* comm = nullptr;
 
+  // CUDA graphs for the launch-bound B = 1 (per-keyframe latency) paths; DV_GRAPHS=0 disables (A/B)
+  bool graphs_on = true;
+
   // stats
   bool stats_on = false;
   double stage_ms[ST_COUNT] = {0, 0, 0, 0, 0, 0};
@@ -129,6 +132,56 @@ struct Engine {
   int upload_f16(const std::vector<float>& v, __half** out);
   int upload_f32(const std::vector<float>& v, float** out);
 };
+
+// One captured-and-instantiated launch sequence.  The B = 1 paths are launch-bound (~130 launches of a few
+// microseconds each per LightGlue match): the sequence is captured ONCE per shape into a CUDA graph - PDL edges
+// included - and replayed with a single cudaGraphLaunch.  Per-call host tables live in pinned memory at fixed
+// addresses and are read by the graph's memcpy nodes at replay time.
+struct GraphCache {
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;        // kernels inside (added to Engine::launches on every replay)
+  bool failed = false;         // capture / instantiation was refused once: stay on the eager path
+  ~GraphCache() { if (exec) cudaGraphExecDestroy(exec); }
+  GraphCache() = default;
+  GraphCache(const GraphCache&) = delete;
+  GraphCache& operator=(const GraphCache&) = delete;
+};
+// enqueue(): queues the whole sequence on e->st and returns a dv_status.  Event-timed modes (stage stats, kernel probe)
+// bypass the graph because they record events between the launches.
+template <class F>
+int run_graphed(Engine* e, GraphCache& gc, F&& enqueue) {
+  if (!e->graphs_on || e->stats_on || e->probe_on || gc.failed) return enqueue();
+  if (!gc.exec) {
+    if (cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      gc.failed = true;
+      return enqueue();
+    }
+    const int64_t l0 = e->launches;
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+    gc.launches = e->launches - l0;
+    e->launches = l0;
+    if (rc != 0 || ce != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      gc.failed = true;
+      return rc != 0 ? rc : enqueue();
+    }
+    const cudaError_t ci = cudaGraphInstantiate(&gc.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ci != cudaSuccess) {
+      cudaGetLastError();
+      gc.exec = nullptr;
+      gc.failed = true;
+      return enqueue();
+    }
+  }
+  e->launches += gc.launches;
+  DV_CUDA_OK(cudaGraphLaunch(gc.exec, e->st));
+  return DV_OK;
+}
 
 // stage timing scope (no-op unless stats are enabled)
 struct ProbeScope {   // event pair around one kernel launch (dominant-kernel roofline probe)

@@ -9,6 +9,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <utility>
 
 #include "engine.h"
 #include "lg.h"
@@ -72,6 +74,7 @@ struct LgNet {
   // staging for the host-vector API
   float *st_k = nullptr, *st_d = nullptr, *h_st_k = nullptr, *h_st_d = nullptr;   // [2*segcap,2], [2*segcap,256]
   int* h_out_i = nullptr; float* h_out_f = nullptr;
+  std::map<std::pair<int, int>, GraphCache> graphs;     // P == 1 launch sequences by (m, n)
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -812,56 +815,67 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     g->h_ju[2 * g->P + 2 * p] = {s0.off, s0.n, s1.off, s1.n, 0, 0, 256, 0};          // cross: qk of the other image, its v
     g->h_ju[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
   }
-  PairDesc* d_pd = reinterpret_cast<PairDesc*>(g->d_segs + 2 * g->P);
-  DV_CUDA_OK(cudaMemcpyAsync(g->d_segs, hs, sizeof(LgSeg) * 3 * g->P, cudaMemcpyHostToDevice, e->st));
-  DV_CUDA_OK(cudaMemcpyAsync(g->jobs_self, hj, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
-  DV_CUDA_OK(cudaMemcpyAsync(g->jobs_cross, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
-  DV_CUDA_OK(cudaMemcpyAsync(g->ju_self, g->h_ju, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
-  DV_CUDA_OK(cudaMemcpyAsync(g->ju_cross, g->h_ju + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
-  k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
-  DV_LAUNCHED(e, 1);
-  if (after_load && *after_load) DV_TRY((*after_load)());
-  const dim3 agrid(cdiv(max_n_any, ATT_QT), LG_HEADS, 2 * P);
-  for (int i = 0; i < LG_LAYERS; ++i) {
-    LgLayer& L = g->L[i];
-    // self block
-    DV_TRY(launch_gemm(L.p_qkv, T, e->st));
-    if (!gemm_is_persistent())
-      k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
-    if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_self, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_self, 0.125f));
-    DV_TRY(launch_gemm(L.p_out, T, e->st));
-    if (g->fused_ffn) {
-      DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
-    } else {
-      DV_TRY(launch_gemm(L.p_f0, T, e->st));
-      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
-                            (const float*)L.ln_b, g->ffg, (int64_t)T));
-      DV_TRY(launch_gemm(L.p_f3, T, e->st));
+  // Everything below only queues work on e->st; the per-call tables above sit in pinned memory at fixed addresses.  A
+  // single pair (the per-keyframe latency path: ~130 launches of a few microseconds each) is captured once per (m, n)
+  // into a CUDA graph and replayed; batched calls amortise their launches over the batch and stay eager.
+  auto enqueue = [&]() -> int {
+    PairDesc* d_pd = reinterpret_cast<PairDesc*>(g->d_segs + 2 * g->P);
+    DV_CUDA_OK(cudaMemcpyAsync(g->d_segs, hs, sizeof(LgSeg) * 3 * g->P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(g->jobs_self, hj, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(g->jobs_cross, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(g->ju_self, g->h_ju, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(g->ju_cross, g->h_ju + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
+    DV_LAUNCHED(e, 1);
+    if (after_load && *after_load) DV_TRY((*after_load)());
+    const dim3 agrid(cdiv(max_n_any, ATT_QT), LG_HEADS, 2 * P);
+    for (int i = 0; i < LG_LAYERS; ++i) {
+      LgLayer& L = g->L[i];
+      // self block
+      DV_TRY(launch_gemm(L.p_qkv, T, e->st));
+      if (!gemm_is_persistent())
+        k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
+      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_self, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+      else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_self, 0.125f));
+      DV_TRY(launch_gemm(L.p_out, T, e->st));
+      if (g->fused_ffn) {
+        DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
+      } else {
+        DV_TRY(launch_gemm(L.p_f0, T, e->st));
+        DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
+                              (const float*)L.ln_b, g->ffg, (int64_t)T));
+        DV_TRY(launch_gemm(L.p_f3, T, e->st));
+      }
+      // cross block
+      DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
+      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_cross, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+      else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_cross, 0.125f));
+      DV_TRY(launch_gemm(L.pc_out, T, e->st));
+      if (g->fused_ffn) {
+        DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
+      } else {
+        DV_TRY(launch_gemm(L.pc_f0, T, e->st));
+        DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
+                              (const float*)L.cln_b, g->ffg, (int64_t)T));
+        DV_TRY(launch_gemm(L.pc_f3, T, e->st));
+      }
+      DV_LAUNCHED(e, 13);
     }
-    // cross block
-    DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
-    if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_cross, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-    else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_cross, 0.125f));
-    DV_TRY(launch_gemm(L.pc_out, T, e->st));
-    if (g->fused_ffn) {
-      DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
-    } else {
-      DV_TRY(launch_gemm(L.pc_f0, T, e->st));
-      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
-                            (const float*)L.cln_b, g->ffg, (int64_t)T));
-      DV_TRY(launch_gemm(L.pc_f3, T, e->st));
-    }
-    DV_LAUNCHED(e, 13);
+    DV_CUDA_OK(cudaGetLastError());
+    DV_TRY(launch_gemm(g->p_final, T, e->st));
+    k_lg_matchability<<<cdiv(T, 8), 256, 0, e->st>>>(g->x32, g->wmatch, g->bmatch, g->z, T);
+    DV_LAUNCHED(e, 2);
+    // sim_p = md0_p md1_p^T for all pairs in ONE batched launch: operands are row windows of the packed md buffer
+    DV_TRY(launch_gemm_batched(g->p_sim, reinterpret_cast<const int4*>(d_pd), P, max_m, max_n, (long)SC * SC, e->st));
+    DV_LAUNCHED(e, 1);
+    return lg_tail(e, P, d_pd, g->d_segs, max_m, max_n, 1);
+  };
+  const bool has_hook = after_load && *after_load;
+  if (P == 1 && !has_hook) {
+    if (g->graphs.size() > 32) g->graphs.clear();
+    return run_graphed(e, g->graphs[std::make_pair(hs[0].n, hs[1].n)], enqueue);
   }
-  DV_CUDA_OK(cudaGetLastError());
-  DV_TRY(launch_gemm(g->p_final, T, e->st));
-  k_lg_matchability<<<cdiv(T, 8), 256, 0, e->st>>>(g->x32, g->wmatch, g->bmatch, g->z, T);
-  DV_LAUNCHED(e, 2);
-  // sim_p = md0_p md1_p^T for all pairs in ONE batched launch: operands are row windows of the packed md buffer
-  DV_TRY(launch_gemm_batched(g->p_sim, reinterpret_cast<const int4*>(d_pd), P, max_m, max_n, (long)SC * SC, e->st));
-  DV_LAUNCHED(e, 1);
-  return lg_tail(e, P, d_pd, g->d_segs, max_m, max_n, 1);
+  return enqueue();
 }
 
 // copies match results of pair p to host buffers (synchronises)

@@ -33,6 +33,7 @@ struct MixNet {
   std::vector<HaloPlan> hplans;        // layer1's 64->64 3x3 convs run on the weights-stationary halo kernel
   std::vector<std::function<int(Engine*, int)>> ops;
   int n_launch = 0;
+  GraphCache g_b1;                     // the whole op list for one frame as a CUDA graph (per-keyframe latency path)
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -574,11 +575,15 @@ int mix_run(Engine* e, int b) {
   if (!m) { set_error("MixVPR not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   StageScope sc(e, ST_MIX);
   e->image_acquire();
-  for (auto& op : m->ops) DV_TRY(op(e, b));
+  auto enqueue = [&]() -> int {
+    for (auto& op : m->ops) DV_TRY(op(e, b));
+    DV_CUDA_OK(cudaGetLastError());
+    DV_LAUNCHED(e, m->n_launch);
+    return DV_OK;
+  };
+  const int rc = b == 1 ? run_graphed(e, m->g_b1, enqueue) : enqueue();
   e->image_release();       // k_mix_pre (first op) was the last reader queued for this buffer
-  DV_CUDA_OK(cudaGetLastError());
-  DV_LAUNCHED(e, m->n_launch);
-  return DV_OK;
+  return rc;
 }
 
 float* mix_gdesc(Engine* e) { return e->mix->gdesc; }

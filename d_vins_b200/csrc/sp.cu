@@ -44,6 +44,7 @@ struct SpNet {
   int* re_n = nullptr;                                  // [B]
   float* re_desc = nullptr;                             // [B,max_vio,256]
   int H8 = 0, W8 = 0;
+  GraphCache g_enc[2], g_det;                           // B = 1 launch sequences (1- / 3-channel frames; detection post-net)
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -606,11 +607,24 @@ void sp_free(Engine* e) {
   e->sp = nullptr;
 }
 
+static int sp_enqueue_encoder(Engine* e, int b, bool release_inline);
+
 int sp_run_encoder(Engine* e, int b) {
   SpNet* s = e->sp;
   if (!s) { set_error("SuperPoint not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   StageScope sc(e, ST_SP_CONV);
   e->image_acquire();
+  if (b == 1) {
+    // per-keyframe latency path: 13 launches replayed as one CUDA graph; the frame-buffer events stay outside of it
+    const int rc = run_graphed(e, s->g_enc[e->img_ch == 3 ? 1 : 0], [&]() { return sp_enqueue_encoder(e, 1, false); });
+    e->image_release();
+    return rc;
+  }
+  return sp_enqueue_encoder(e, b, true);
+}
+
+static int sp_enqueue_encoder(Engine* e, int b, bool release_inline) {
+  SpNet* s = e->sp;
   const int H = e->H, W = e->W;
   const int64_t npix = (int64_t)b * H * W;
   k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
@@ -644,7 +658,7 @@ int sp_run_encoder(Engine* e, int b) {
     DV_TRY(launch_gemm(s->p2a, b, e->st));
     DV_TRY(launch_gemm(s->p2b, b, e->st));
   }
-  e->image_release();     // k_gray / the fused conv1a+conv1b kernel were the encoder's only readers of the u8 frames
+  if (release_inline) e->image_release();     // k_gray / the fused conv1a+conv1b kernel were the encoder's only readers of the u8 frames
   if (s->use_halo128) {
     DV_TRY(launch_conv_halo128(s->h3a, b, e->st));
     DV_TRY(launch_conv_halo128(s->h3b, b, e->st));
@@ -677,9 +691,17 @@ static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
   return DV_OK;
 }
 
+static int sp_enqueue_detect(Engine* e, int b);
+
 int sp_run_detect(Engine* e, int b) {
   SpNet* s = e->sp;
   StageScope sc(e, ST_SP_POST);
+  if (b == 1) return run_graphed(e, s->g_det, [&]() { return sp_enqueue_detect(e, 1); });
+  return sp_enqueue_detect(e, b);
+}
+
+static int sp_enqueue_detect(Engine* e, int b) {
+  SpNet* s = e->sp;
   const int ncells = b * e->h8 * e->w8;
   k_softmax_d2s<<<cdiv(ncells, 8), 256, 0, e->st>>>(s->logits, 80, s->smap, ncells, e->h8, e->w8);
   DV_TRY(run_post(e, b, s->smap, s->nms));

@@ -581,7 +581,7 @@ dv_status dv_batch_match_ex(dv_engine* h, int32_t b, const int64_t* query_ids, c
     DV_LAUNCHED(e, 1);
     return DV_OK;
   };
-  DV_TRY(lg_run(e, (int)which.size(), segs.data(), &after_load));
+  DV_TRY(lg_run(e, (int)which.size(), segs.data(), n_pull ? &after_load : nullptr));
   DV_TRY(lg_fetch_batch(e, (int)which.size(), V, which.data(), matches, mscores, k_out));
   // a remote keyframe whose slot was being rewritten while it was read is reported like a non-resident one
   for (int j = 0; j < n_pull; ++j)
