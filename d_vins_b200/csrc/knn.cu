@@ -140,19 +140,28 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_scan(const float* __rest
 #pragma unroll
   for (int t = 0; t < K; ++t) { sD[myq][warp * 4 + myslot][t] = D[t]; sI[myq][warp * 4 + myslot][t] = I[t]; }
   __syncthreads();
-  if (threadIdx.x < nqb) {
-    const int j = threadIdx.x;
+  // per-block merge: warp j merges the 32 candidate lists (8 warps x 4 row slots) of query j - one list per lane, then a
+  // shuffle tree (the serial 8-thread version cost more than the scan itself on 10k-row banks)
+  if (warp < nqb) {
+    const int j = warp;
     float bD[K]; long long bI[K];
 #pragma unroll
-    for (int t = 0; t < K; ++t) { bD[t] = -INFINITY; bI[t] = -1; }
-    for (int w = 0; w < KNN_WARPS * 4; ++w)
+    for (int t = 0; t < K; ++t) { bD[t] = sD[j][lane][t]; bI[t] = sI[j][lane][t]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      float oD[K]; long long oI[K];
+#pragma unroll
+      for (int t = 0; t < K; ++t) { oD[t] = __shfl_xor_sync(0xffffffffu, bD[t], o); oI[t] = __shfl_xor_sync(0xffffffffu, bI[t], o); }
 #pragma unroll
       for (int t = 0; t < K; ++t)
-        if (sI[j][w][t] >= 0) topk_insert<K>(bD, bI, sD[j][w][t], sI[j][w][t]);
+        if (oI[t] >= 0) topk_insert<K>(bD, bI, oD[t], oI[t]);
+    }
+    if (lane == 0) {
 #pragma unroll
-    for (int t = 0; t < K; ++t) {
-      partD[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bD[t];
-      partI[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bI[t];
+      for (int t = 0; t < K; ++t) {
+        partD[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bD[t];
+        partI[((int64_t)(q0 + j) * nblocks + blockIdx.x) * K + t] = bI[t];
+      }
     }
   }
   if (!FUSED) return;
@@ -298,7 +307,12 @@ static int bank_search_impl(Engine* e, const float* d_q, int nq, const int64_t* 
   long long* oI = fused ? b->h_I : b->outI;
   static int dev_sms = 0;
   if (!dev_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int nblocks = (int)std::min<int64_t>(cdiv64(maxlim, KNN_ROWS_PER_BLOCK), (int64_t)dev_sms * 2);   // 128 registers x 256 threads: two resident blocks per SM
+  // 128 registers x 256 threads: two resident blocks per SM.  ONE wave over all query groups: a batch of 64 queries is
+  // 8 query groups, each scanning the bank with (2 * SMs) / 8 fat blocks instead of 8 x (rows / 64) thin ones whose
+  // prologue (query staging) and merge dominated on 10k-row banks (r02: 100 us per 64-query search at 12k rows).
+  const int groups = cdiv(nq, KNN_QB);
+  const int wave = std::max(1, (dev_sms * 2) / groups);
+  const int nblocks = (int)std::min<int64_t>(cdiv64(maxlim, KNN_ROWS_PER_BLOCK), (int64_t)wave);
   switch (k) {
 #define DV_KNN_CASE(KK) case KK: knn_launch<KK>(e, b->rows, d_q, d_nb, lim, nq, nblocks, b->partD, b->partI, b->d_ticket, oD, oI, fused, e->st); break;
     DV_KNN_CASE(1) DV_KNN_CASE(2) DV_KNN_CASE(3) DV_KNN_CASE(4) DV_KNN_CASE(5) DV_KNN_CASE(6) DV_KNN_CASE(7)

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(1024) k_lg_extract(const PairDesc* __restrict_
                                                      const float* __restrict__ max0, int segcap, float thresh,
                                                      const float* __restrict__ kpts, int* __restrict__ matches,
                                                      float* __restrict__ mscores, float* __restrict__ mk0,
-                                                     float* __restrict__ mk1, int* __restrict__ kcount) {
+                                                     float* __restrict__ mk1, int* __restrict__ kcount, int out_base) {
   __shared__ int wsum[32];
   __shared__ int base_s;
   const int pi = blockIdx.x;
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(1024) k_lg_extract(const PairDesc* __restrict_
     const int base = base_s;
     if (valid) {
       const int k = base + woff + wpre;
-      const int64_t o = (int64_t)pi * segcap + k;
+      const int64_t o = (int64_t)(pi + out_base) * segcap + k;
       matches[o * 2] = i; matches[o * 2 + 1] = j;
       mscores[o] = ms;
       const LgSeg s0 = segs[pi * 2], s1 = segs[pi * 2 + 1];
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(1024) k_lg_extract(const PairDesc* __restrict_
     if (tid == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += wsum[w]; base_s = base + tot; }
     __syncthreads();
   }
-  if (tid == 0) kcount[pi] = base_s;
+  if (tid == 0) kcount[pi + out_base] = base_s;
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -760,7 +760,7 @@ void lg_free(Engine* e) {
   e->lg = nullptr;
 }
 
-static int lg_tail(Engine* e, int P, const PairDesc* d_pd, const LgSeg* d_segs, int max_m, int max_n, int compute) {
+static int lg_tail(Engine* e, int P, const PairDesc* d_pd, const LgSeg* d_segs, int max_m, int max_n, int compute, int out_base = 0) {
   LgNet* g = e->lg;
   const int SC = g->segcap;
   const int64_t ps = (int64_t)SC * SC;
@@ -772,21 +772,28 @@ static int lg_tail(Engine* e, int P, const PairDesc* d_pd, const LgSeg* d_segs, 
                                                           compute, g->m0, g->max0);
   k_lg_colmax<<<dim3(cdiv(max_n, 32), P), 256, 0, e->st>>>(g->Lm, SC, ps, d_pd, SC, g->m1);
   k_lg_extract<<<P, 1024, 0, e->st>>>(d_pd, d_segs, g->m0, g->m1, g->max0, SC, e->cfg.lg_filter_thresh, g->kpts,
-                                      g->matches, g->mscores, g->mk0, g->mk1, g->kcount);
+                                      g->matches, g->mscores, g->mk0, g->mk1, g->kcount, out_base);
   DV_CUDA_OK(cudaGetLastError());
   DV_LAUNCHED(e, compute ? 5 : 3);
   return DV_OK;
 }
 
 // segs: host array [2P] with device pointers to keypoints / descriptors; results stay on the device.
-int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* after_load) {
+int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* after_load, int out_base) {
   LgNet* g = e->lg;
   if (!g) { set_error("LightGlue not initialised (engine created without weights)"); return DV_ERR_INVALID; }
-  if (P < 1 || P > g->P) { set_error("lg_run: pair count exceeds max_batch"); return DV_ERR_CAPACITY; }
+  if (P < 1 || out_base < 0 || out_base + P > g->P) { set_error("lg_run: pair count exceeds max_batch"); return DV_ERR_CAPACITY; }
   StageScope sc(e, ST_LG);
   const int SC = g->segcap;
-  LgSeg* hs = g->h_segs;
-  PairDesc* hp = reinterpret_cast<PairDesc*>(hs + 2 * g->P);
+  // Per-call tables (pinned host + device): pair p of this call uses the entries of global pair slot out_base + p, so
+  // the chunks of one batch never overwrite each other's tables while earlier chunks' copies are still queued.
+  LgSeg* hs = g->h_segs + 2 * out_base;
+  PairDesc* hp = reinterpret_cast<PairDesc*>(g->h_segs + 2 * g->P) + out_base;
+  AttnJob* hj = g->h_jobs + 2 * out_base;                  // self jobs; cross jobs at + 2 * g->P
+  AttnJobU* hu = g->h_ju + 2 * out_base;
+  LgSeg* d_segs = g->d_segs + 2 * out_base;
+  AttnJob *d_js = g->jobs_self + 2 * out_base, *d_jc = g->jobs_cross + 2 * out_base;
+  AttnJobU *d_us = g->ju_self + 2 * out_base, *d_uc = g->ju_cross + 2 * out_base;
   int off = 0, max_n_any = 0, max_m = 0, max_n = 0;
   for (int i = 0; i < 2 * P; ++i) {
     hs[i] = segs_in[i];
@@ -796,7 +803,6 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     max_n_any = std::max(max_n_any, hs[i].n);
   }
   const int T = off;
-  AttnJob* hj = g->h_jobs;
   for (int p = 0; p < P; ++p) {
     const LgSeg &s0 = hs[2 * p], &s1 = hs[2 * p + 1];
     hp[p] = {s0.off, s1.off, s0.n, s1.n};
@@ -806,26 +812,27 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       const LgSeg& s = hs[2 * p + k];
       __half* base = g->qkv + (int64_t)s.off * 768;
       hj[2 * p + k] = {base, base + 256, base + 512, g->ctx + (int64_t)s.off * 256, s.n, s.n, 768, 768, 768, 256};
-      g->h_ju[2 * p + k] = {s.off, s.n, s.off, s.n, 0, 256, 512, 0};
+      hu[2 * p + k] = {s.off, s.n, s.off, s.n, 0, 256, 512, 0};
     }
     __half* b0 = g->qkv + (int64_t)s0.off * 768;
     __half* b1 = g->qkv + (int64_t)s1.off * 768;
     hj[2 * g->P + 2 * p] = {b0, b1, b1 + 256, g->ctx + (int64_t)s0.off * 256, s0.n, s1.n, 768, 768, 768, 256};
     hj[2 * g->P + 2 * p + 1] = {b1, b0, b0 + 256, g->ctx + (int64_t)s1.off * 256, s1.n, s0.n, 768, 768, 768, 256};
-    g->h_ju[2 * g->P + 2 * p] = {s0.off, s0.n, s1.off, s1.n, 0, 0, 256, 0};          // cross: qk of the other image, its v
-    g->h_ju[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
+    hu[2 * g->P + 2 * p] = {s0.off, s0.n, s1.off, s1.n, 0, 0, 256, 0};          // cross: qk of the other image, its v
+    hu[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
   }
   // Everything below only queues work on e->st; the per-call tables above sit in pinned memory at fixed addresses.  A
   // single pair (the per-keyframe latency path: ~130 launches of a few microseconds each) is captured once per (m, n)
   // into a CUDA graph and replayed; batched calls amortise their launches over the batch and stay eager.
   auto enqueue = [&]() -> int {
-    PairDesc* d_pd = reinterpret_cast<PairDesc*>(g->d_segs + 2 * g->P);
-    DV_CUDA_OK(cudaMemcpyAsync(g->d_segs, hs, sizeof(LgSeg) * 3 * g->P, cudaMemcpyHostToDevice, e->st));
-    DV_CUDA_OK(cudaMemcpyAsync(g->jobs_self, hj, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
-    DV_CUDA_OK(cudaMemcpyAsync(g->jobs_cross, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
-    DV_CUDA_OK(cudaMemcpyAsync(g->ju_self, g->h_ju, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
-    DV_CUDA_OK(cudaMemcpyAsync(g->ju_cross, g->h_ju + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
-    k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(g->d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
+    PairDesc* d_pd = reinterpret_cast<PairDesc*>(g->d_segs + 2 * g->P) + out_base;
+    DV_CUDA_OK(cudaMemcpyAsync(d_segs, hs, sizeof(LgSeg) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(d_pd, hp, sizeof(PairDesc) * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(d_js, hj, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(d_jc, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(d_us, hu, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    DV_CUDA_OK(cudaMemcpyAsync(d_uc, hu + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
     DV_LAUNCHED(e, 1);
     if (after_load && *after_load) DV_TRY((*after_load)());
     const dim3 agrid(cdiv(max_n_any, ATT_QT), LG_HEADS, 2 * P);
@@ -835,8 +842,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       DV_TRY(launch_gemm(L.p_qkv, T, e->st));
       if (!gemm_is_persistent())
         k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
-      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_self, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-      else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_self, 0.125f));
+      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+      else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_js, 0.125f));
       DV_TRY(launch_gemm(L.p_out, T, e->st));
       if (g->fused_ffn) {
         DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
@@ -848,8 +855,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       }
       // cross block
       DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
-      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, g->ju_cross, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
-      else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)g->jobs_cross, 0.125f));
+      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+      else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_jc, 0.125f));
       DV_TRY(launch_gemm(L.pc_out, T, e->st));
       if (g->fused_ffn) {
         DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
@@ -868,10 +875,10 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     // sim_p = md0_p md1_p^T for all pairs in ONE batched launch: operands are row windows of the packed md buffer
     DV_TRY(launch_gemm_batched(g->p_sim, reinterpret_cast<const int4*>(d_pd), P, max_m, max_n, (long)SC * SC, e->st));
     DV_LAUNCHED(e, 1);
-    return lg_tail(e, P, d_pd, g->d_segs, max_m, max_n, 1);
+    return lg_tail(e, P, d_pd, d_segs, max_m, max_n, 1, out_base);
   };
   const bool has_hook = after_load && *after_load;
-  if (P == 1 && !has_hook) {
+  if (P == 1 && !has_hook && out_base == 0) {
     if (g->graphs.size() > 32) g->graphs.clear();
     return run_graphed(e, g->graphs[std::make_pair(hs[0].n, hs[1].n)], enqueue);
   }

@@ -22,7 +22,9 @@ struct AttnJobU { int q_row, nq, k_row, nk, q_col, k_col, v_col, pad; };
 
 // segs [2P]: (query, old) per pair; results stay on device.  `after_load` (optional) is invoked right after the kernel
 // that reads the callers' keypoint / descriptor pointers has been queued (store.cu verifies remote reads there).
-int lg_run(Engine* e, int P, const LgSeg* segs, const std::function<int()>* after_load = nullptr);
+// `out_base`: first output slot (matches / mscores / kcount of pair p land at slot out_base + p), so a batch processed
+// in several chunks is fetched with ONE lg_fetch_batch at the end.
+int lg_run(Engine* e, int P, const LgSeg* segs, const std::function<int()>* after_load = nullptr, int out_base = 0);
 int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out);
 int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float* mk0, float* mk1, int32_t* k_out);
 

@@ -4,6 +4,7 @@
 // feature-mixer aggregator (LayerNorm -> GEMM+ReLU -> GEMM+residual, channel_proj GEMM, row_proj + L2 kernel).
 // Architecture restated from amaralibey/MixVPR + torchvision (un-vendored; see oracle/mixvpr.py).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <functional>
@@ -11,6 +12,8 @@
 #include "engine.h"
 
 namespace dv {
+
+#define DV_MIX_CHUNK_DEFAULT 0
 
 struct MixNet {
   // parameters (device)
@@ -33,7 +36,10 @@ struct MixNet {
   std::vector<HaloPlan> hplans;        // layer1's 64->64 3x3 convs run on the weights-stationary halo kernel
   std::vector<std::function<int(Engine*, int)>> ops;
   int n_launch = 0;
-  GraphCache g_b1;                     // the whole op list for one frame as a CUDA graph (per-keyframe latency path)
+  int frame_off = 0;                   // first frame of the chunk being processed (mix_run chunks the batch)
+  int chunk = 0;                       // DV_MIX_CHUNK: frames per pass over the op list (0 = the whole batch)
+  GraphCache g_b1[2][2];               // the whole op list for one frame as a CUDA graph (per-keyframe latency path),
+                                       // one per [frame buffer][1- / 3-channel]: the frame pointer is baked into the graph
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -389,12 +395,13 @@ int mix_init(Engine* e) {
     return ep;
   };
 
+  { const char* env = getenv("DV_MIX_CHUNK"); m->chunk = env ? atoi(env) : DV_MIX_CHUNK_DEFAULT; }
   const std::string pre = "mix.backbone.model.";
   // ---- pre-processing + stem
   m->ops.push_back([](Engine* en, int b) {
     MixNet* mm = en->mix;
     const int total = b * 320 * 320;
-    k_mix_pre<<<cdiv(total, 256), 256, 0, en->st>>>(en->d_img, en->H, en->W, en->img_ch, mm->d2i[0], mm->d2i[1],
+    k_mix_pre<<<cdiv(total, 256), 256, 0, en->st>>>(en->d_img + (size_t)mm->frame_off * en->H * en->W * en->img_ch, en->H, en->W, en->img_ch, mm->d2i[0], mm->d2i[1],
                                                    mm->d2i[2], mm->d2i[3], mm->d2i[4], mm->d2i[5], mm->img16, total);
     if (mm->fused_stem) return launch_stem_conv(mm->stem, b, en->st);
     k_im2col_stem<<<dim3(160 / STEM_OXB, 160, b), 256, 0, en->st>>>(mm->img16, mm->col);
@@ -553,7 +560,7 @@ int mix_init(Engine* e) {
     DV_TRY(e->upload_f32(br->data, &m->row_b));
     m->ops.push_back([](Engine* en, int b) {
       MixNet* mm = en->mix;
-      k_rowproj_norm<<<b, 1024, 0, en->st>>>(mm->y32, mm->row_w, mm->row_b, mm->gdesc, 400);
+      k_rowproj_norm<<<b, 1024, 0, en->st>>>(mm->y32, mm->row_w, mm->row_b, mm->gdesc + (size_t)mm->frame_off * 512, 400);
       return (int)DV_OK;
     });
     m->n_launch++;
@@ -575,13 +582,22 @@ int mix_run(Engine* e, int b) {
   if (!m) { set_error("MixVPR not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   StageScope sc(e, ST_MIX);
   e->image_acquire();
+  // The op list runs over the batch in chunks of `chunk` frames: every ResNet activation of a chunk then fits the
+  // 126 MB L2 between producer and consumer kernels (at 64 frames a layer1 tensor alone is 210 MB and every 1x1 / 3x3
+  // kernel streams its operands from HBM).  Only the first op (frame pointer) and the last (descriptor row) see the offset.
   auto enqueue = [&]() -> int {
-    for (auto& op : m->ops) DV_TRY(op(e, b));
+    const int step = (m->chunk > 0 && m->chunk < b) ? m->chunk : b;
+    for (int f0 = 0; f0 < b; f0 += step) {
+      m->frame_off = f0;
+      const int nb = std::min(step, b - f0);
+      for (auto& op : m->ops) DV_TRY(op(e, nb));
+      DV_LAUNCHED(e, m->n_launch);
+    }
+    m->frame_off = 0;
     DV_CUDA_OK(cudaGetLastError());
-    DV_LAUNCHED(e, m->n_launch);
     return DV_OK;
   };
-  const int rc = b == 1 ? run_graphed(e, m->g_b1, enqueue) : enqueue();
+  const int rc = b == 1 ? run_graphed(e, m->g_b1[e->img_idx][e->img_ch == 3 ? 1 : 0], enqueue) : enqueue();
   e->image_release();       // k_mix_pre (first op) was the last reader queued for this buffer
   return rc;
 }

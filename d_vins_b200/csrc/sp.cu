@@ -10,6 +10,8 @@
 
 namespace dv {
 
+#define DV_NMS_DEFAULT_LARGE false
+
 struct SpNet {
   // weights
   float *w1a = nullptr, *b1a = nullptr;                 // conv1a fp32 [64,9],[64]
@@ -26,6 +28,7 @@ struct SpNet {
   HaloPlan h1b, h2a, h2b;                               // weights-stationary halo kernels for the 64->64 layers
   Halo128Plan h3a, h3b, h4a, h4b, hPD;                  // 256-pixel halo tiles, streamed weights (conv_halo128.cu)
   bool use_halo128 = false;
+  bool nms_large = false;                               // DV_NMS_TILE=L / S: 128x64 or 64x32 NMS tiles (A/B)
   bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
   int fuse1a_tc = 0;                                    // DV_SP_FUSE1A=2: conv1a on the tensor cores inside conv1b (conv_halo.cu FUSE == 2)
   bool fuse1a = false;                                  // DV_SP_FUSE1A=1: conv1a inside conv1b's producer (correct, but the
@@ -44,7 +47,7 @@ struct SpNet {
   int* re_n = nullptr;                                  // [B]
   float* re_desc = nullptr;                             // [B,max_vio,256]
   int H8 = 0, W8 = 0;
-  GraphCache g_enc[2], g_det;                           // B = 1 launch sequences (1- / 3-channel frames; detection post-net)
+  GraphCache g_enc[2][2], g_det;                        // B = 1 launch sequences: [1- / 3-channel][frame buffer]; detection post-net
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -192,12 +195,20 @@ __global__ void k_softmax_d2s(const float* __restrict__ logits, int ld, float* _
 // simple_nms (export/superpoint.py:52-69), radius 4, two refinement rounds, fused into one tile kernel.
 // Dependency radius = 4 + 8 + 8 = 20, so each 64x32 output tile loads a 104x72 region.  Separable 9-tap max in
 // shared memory; pixels outside the image are -inf and never "maxima" (== torch's implicit -inf padding).
-#define NMS_TW 64
-#define NMS_TH 32
 #define NMS_HALO 20
-#define NMS_RW (NMS_TW + 2 * NMS_HALO)
-#define NMS_RH (NMS_TH + 2 * NMS_HALO)
-#define NMS_RN (NMS_RW * NMS_RH)
+// Tile configuration: TW x TH output pixels per CTA, (TW + 40) x (TH + 40) region in shared memory (10 bytes / pixel),
+// ROW_STRIP / COL_STRIP outputs per thread in the row / column passes (must divide the region width / height).
+//   NmsCfgS: 64 x 32 tiles, 104 x 72 region (3.65x the tile), 75 KB, 320 threads, three CTAs per SM          (r01)
+//   NmsCfgL: 128 x 64 tiles, 168 x 104 region (2.13x the tile), 171 KB, 768 threads, one CTA per SM: 1.7x fewer
+//            region pixels per frame through the ten separable passes
+struct NmsCfgS { static constexpr int TW = 64, TH = 32, THREADS = 320, ROW_STRIP = 26, COL_STRIP = 24; };
+struct NmsCfgL { static constexpr int TW = 128, TH = 64, THREADS = 768, ROW_STRIP = 24, COL_STRIP = 26; };
+template <class C> struct NmsDims {
+  static constexpr int RW = C::TW + 2 * NMS_HALO, RH = C::TH + 2 * NMS_HALO, RN = RW * RH;
+  static constexpr int SMEM = RN * (2 * 4 + 2);
+  static_assert(RW % C::ROW_STRIP == 0 && RH % C::COL_STRIP == 0, "strips must tile the region");
+  static_assert(RH * (RW / C::ROW_STRIP) <= C::THREADS && RW * (RH / C::COL_STRIP) <= C::THREADS, "one strip per thread");
+};
 
 // 9-tap running max over a strip of L outputs in registers: 4 max ops per output (pairwise doubling) and ONE shared
 // memory load per input instead of 9.  Taps outside [0, n) are -inf (region edge == torch's implicit -inf padding).
@@ -224,13 +235,11 @@ __device__ __forceinline__ void strip_max9(LD ld, ST st, int p0, int n) {
   }
 }
 
-#define NMS_THREADS 320
-#define NMS_ROW_STRIP 26     // 104 = 4 x 26
-#define NMS_COL_STRIP 24     // 72  = 3 x 24
 
 // 9x9 max-pool of the region: T1 = rowmax(in(i)); out(i, colmax(T1)); both functors take the linear region index.
-template <class IN, class OUT>
+template <class C, class IN, class OUT>
 __device__ __forceinline__ void maxpool9(IN in, OUT out, float* T1) {
+  constexpr int NMS_RW = NmsDims<C>::RW, NMS_RH = NmsDims<C>::RH, NMS_ROW_STRIP = C::ROW_STRIP, NMS_COL_STRIP = C::COL_STRIP;
   {
     const int t = threadIdx.x;
     if (t < NMS_RH * (NMS_RW / NMS_ROW_STRIP)) {
@@ -252,9 +261,11 @@ __device__ __forceinline__ void maxpool9(IN in, OUT out, float* T1) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NMS_THREADS) k_nms_select(const float* __restrict__ smap, float* __restrict__ nms_out,
+template <class C>
+__global__ void __launch_bounds__(C::THREADS) k_nms_select(const float* __restrict__ smap, float* __restrict__ nms_out,
                                                     unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
                                                     int H8, int W8, int border, float thresh) {
+  constexpr int NMS_TW = C::TW, NMS_TH = C::TH, NMS_RW = NmsDims<C>::RW, NMS_RN = NmsDims<C>::RN;
   extern __shared__ float sm[];
   float* S = sm;
   float* T1 = S + NMS_RN;
@@ -273,15 +284,15 @@ __global__ void __launch_bounds__(NMS_THREADS) k_nms_select(const float* __restr
   __syncthreads();
   // export/superpoint.py:52-66 simple_nms: max_mask = scores == max_pool(scores); two rounds of
   // supp = max_pool(mask) > 0; supp_scores = where(supp, 0, scores); mask |= (supp_scores == max_pool(supp_scores)) & ~supp
-  maxpool9([&](int i) { return S[i]; },
+  maxpool9<C>([&](int i) { return S[i]; },
            [&](int i, float m) {
              const float v = S[i];
              MM[i] = (v != NEG) && (v == m);
            },
            T1);
   for (int round = 0; round < 2; ++round) {
-    maxpool9([&](int i) { return MM[i] ? 1.f : 0.f; }, [&](int i, float m) { SUPP[i] = m > 0.f; }, T1);
-    maxpool9(
+    maxpool9<C>([&](int i) { return MM[i] ? 1.f : 0.f; }, [&](int i, float m) { SUPP[i] = m > 0.f; }, T1);
+    maxpool9<C>(
         [&](int i) {
           const float v = S[i];
           return (v == NEG) ? NEG : (SUPP[i] ? 0.f : v);
@@ -579,8 +590,9 @@ int sp_init(Engine* e) {
     EpiParams ed; ed.out32 = s->dmap; ed.ld32 = 256; ed.bias = s->bDb;
     DV_TRY(plan_gemm(&s->pDb, s->aPD + 256, 512, (int)P8, s->wDb, 256, 256, 256, ed));
   }
-  DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  NMS_RN * (2 * 4 + 2)));
+  DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select<NmsCfgS>, cudaFuncAttributeMaxDynamicSharedMemorySize, NmsDims<NmsCfgS>::SMEM));
+  DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select<NmsCfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, NmsDims<NmsCfgL>::SMEM));
+  { const char* env = getenv("DV_NMS_TILE"); s->nms_large = env ? env[0] == 'L' : DV_NMS_DEFAULT_LARGE; }
   // debug views
   e->dbg["gray"] = {s->gray, (int64_t)H * W, 0};
   e->dbg[s->use_halo ? "conv1a_blocked" : "conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
@@ -615,8 +627,9 @@ int sp_run_encoder(Engine* e, int b) {
   StageScope sc(e, ST_SP_CONV);
   e->image_acquire();
   if (b == 1) {
-    // per-keyframe latency path: 13 launches replayed as one CUDA graph; the frame-buffer events stay outside of it
-    const int rc = run_graphed(e, s->g_enc[e->img_ch == 3 ? 1 : 0], [&]() { return sp_enqueue_encoder(e, 1, false); });
+    // per-keyframe latency path: 13 launches replayed as one CUDA graph; the frame-buffer events stay outside of it.
+    // The frame pointer is a kernel argument baked into the graph and frames are double-buffered: one graph per buffer.
+    const int rc = run_graphed(e, s->g_enc[e->img_ch == 3 ? 1 : 0][e->img_idx], [&]() { return sp_enqueue_encoder(e, 1, false); });
     e->image_release();
     return rc;
   }
@@ -683,8 +696,12 @@ static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
   SpNet* s = e->sp;
   const int H8 = s->H8, W8 = s->W8, K = e->cfg.max_kpts;
   DV_CUDA_OK(cudaMemsetAsync(s->cand_cnt, 0, sizeof(int) * b, e->st));
-  k_nms_select<<<dim3(cdiv(W8, NMS_TW), cdiv(H8, NMS_TH), b), NMS_THREADS, NMS_RN * (2 * 4 + 2), e->st>>>(
-      smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
+  if (s->nms_large)
+    k_nms_select<NmsCfgL><<<dim3(cdiv(W8, NmsCfgL::TW), cdiv(H8, NmsCfgL::TH), b), NmsCfgL::THREADS, NmsDims<NmsCfgL>::SMEM, e->st>>>(
+        smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
+  else
+    k_nms_select<NmsCfgS><<<dim3(cdiv(W8, NmsCfgS::TW), cdiv(H8, NmsCfgS::TH), b), NmsCfgS::THREADS, NmsDims<NmsCfgS>::SMEM, e->st>>>(
+        smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
   k_topk<<<b, 1024, 0, e->st>>>(s->cand, s->cand_cnt, H8 * W8, K, W8, s->kpts, s->kpts_f, s->scores, s->n_kpts);
   DV_CUDA_OK(cudaGetLastError());
   DV_LAUNCHED(e, 2);

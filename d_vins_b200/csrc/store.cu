@@ -1,6 +1,7 @@
 // Device-resident keyframe feature store + the batched keyframe-round API (throughput path, SURVEY §8(e),(f)-1).
 // A keyframe's local features never leave the GPU between extraction and matching: kpts = SP ++ VIO points,
 // desc = SP descriptors ++ SP_RE descriptors - the concatenation contract of keyframe.cpp:401-432.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -10,6 +11,8 @@
 
 #include "engine.h"
 #include "lg.h"
+
+#define DV_LG_CHUNK_DEFAULT 0
 
 namespace dv {
 
@@ -581,7 +584,12 @@ dv_status dv_batch_match_ex(dv_engine* h, int32_t b, const int64_t* query_ids, c
     DV_LAUNCHED(e, 1);
     return DV_OK;
   };
-  DV_TRY(lg_run(e, (int)which.size(), segs.data(), n_pull ? &after_load : nullptr));
+  // DV_LG_CHUNK pairs per LightGlue pass (0 = all): smaller chunks keep the token buffers of a pass inside the L2
+  static const int lg_chunk = [] { const char* env = getenv("DV_LG_CHUNK"); return env ? atoi(env) : DV_LG_CHUNK_DEFAULT; }();
+  const int Pn = (int)which.size();
+  const int step = (lg_chunk > 0 && lg_chunk < Pn) ? lg_chunk : Pn;
+  for (int p0 = 0; p0 < Pn; p0 += step)
+    DV_TRY(lg_run(e, std::min(step, Pn - p0), segs.data() + 2 * p0, (n_pull && p0 + step >= Pn) ? &after_load : nullptr, p0));   // seqlock check after the LAST load
   DV_TRY(lg_fetch_batch(e, (int)which.size(), V, which.data(), matches, mscores, k_out));
   // a remote keyframe whose slot was being rewritten while it was read is reported like a non-resident one
   for (int j = 0; j < n_pull; ++j)

@@ -1,6 +1,8 @@
 #include <algorithm>
 #include <stdlib.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "engine.h"
 
 namespace dv {
@@ -48,7 +50,11 @@ int Engine::upload_f32(const std::vector<float>& v, float** out) {
   return DV_OK;
 }
 
+// NVTX range per pipeline stage (SURVEY §5 tracing): header-only nvtx3, a no-op unless a profiler injected itself
+static const char* const kStageName[ST_COUNT] = {"dv.sp_convs", "dv.sp_post", "dv.mixvpr", "dv.knn", "dv.lightglue", "dv.copies"};
+
 StageScope::StageScope(Engine* e_, int s) : e(e_), stage(s) {
+  nvtxRangePushA(kStageName[s]);
   if (!e->stats_on) return;
   auto get = [&]() {
     cudaEvent_t ev;
@@ -60,6 +66,7 @@ StageScope::StageScope(Engine* e_, int s) : e(e_), stage(s) {
   cudaEventRecord(a, e->st);
 }
 StageScope::~StageScope() {
+  nvtxRangePop();
   if (!a) return;
   cudaEventRecord(b, e->st);
   e->pending.push_back({stage, a, b});

@@ -71,6 +71,8 @@ def heads_q(w, feat: torch.Tensor, keep=None):
     cDa = h16(F.relu(F.conv2d(feat, _w16(w, "convDa.weight"), _b(w, "convDa.bias"), padding=1)))
     d = F.conv2d(cDa, _w16(w, "convDb.weight"), _b(w, "convDb.bias"))
     if keep is not None:
+        keep["convPa"] = cPa
+        keep["convDa"] = cDa
         keep["logits"] = logits
         keep["convDb"] = d
     s = F.softmax(logits, 1)[:, :-1]

@@ -106,3 +106,29 @@ int use(Estimator_net::Estimator* e, MixVPR_net::MixVPR* m, const cv::Mat& img, 
                             str(tmp_path / "o.o")] + inc, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
     assert os.path.exists(build.build_stream_demo())
+
+
+def test_checkpoint_converter_contract(tmp_path):
+    """d_vins_b200.convert_weights maps upstream state_dict keys to the DVWGT001 file the engine loads: its key / shape
+    contract equals the synthetic weight set every test runs on, a torch-saved state_dict (plain and Lightning-style)
+    converts to a byte-identical tensor set, and a missing tensor is an error."""
+    import numpy as np
+    import torch
+    from d_vins_b200 import convert_weights as cw
+    from oracle import weights
+    W = weights.synth_all()
+    want = cw.expected_keys()
+    assert set(want) == set(W) and all(tuple(W[k].shape) == want[k] for k in want)
+    sp = {k: torch.from_numpy(v) for k, v in weights.sub(W, "sp.").items()}
+    lg = {k: torch.from_numpy(v) for k, v in weights.sub(W, "lg.").items()}
+    lg["transformers.0.token_confidence.0.weight"] = torch.zeros(1, 256)        # unused upstream tensors are ignored
+    mix = {"state_dict": {k: torch.from_numpy(v) for k, v in weights.sub(W, "mix.").items()}}
+    torch.save(sp, tmp_path / "sp.pth"); torch.save(lg, tmp_path / "lg.pth"); torch.save(mix, tmp_path / "mix.ckpt")
+    out = cw.convert(str(tmp_path / "sp.pth"), str(tmp_path / "lg.pth"), str(tmp_path / "mix.ckpt"))
+    cw.save_dvw(str(tmp_path / "w.dvw"), out)
+    back = weights.load_weights(str(tmp_path / "w.dvw"))
+    assert list(back) == list(want) and all(np.array_equal(back[k], W[k]) for k in W)
+    del sp["convDb.bias"]
+    torch.save(sp, tmp_path / "bad.pth")
+    with pytest.raises(KeyError):
+        cw.convert(superpoint=str(tmp_path / "bad.pth"))

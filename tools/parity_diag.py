@@ -49,8 +49,27 @@ def main():
         r = e.sp_detect()
         r["score_map_dbg"] = e.dbg_read("score_map").reshape(H // 8 * 8, Wd // 8 * 8)
         o32 = osp.superpoint(ws, img)
-        oq = quant.superpoint_q(ws, img)
+        keepq = {}
+        oq = quant.superpoint_q(ws, img, keep=keepq)
         out[name] = {"vs_fp32": kp_stats(o32, r), "vs_quant": kp_stats(oq, r)}
+        if name in ("euroc", "kitti"):
+            # per-layer fidelity of the quantisation-aware oracle: fraction of fp16 activations that are bit-identical
+            layers = {}
+            for nm in ("conv1b_pool", "conv2a", "conv2b_pool", "conv3a", "conv3b_pool", "conv4a", "conv4b"):
+                ref = keepq[nm][0].permute(1, 2, 0).numpy()
+                hh, ww, cc = ref.shape
+                got = e.dbg_read(nm + "_blocked").reshape(cc // 8, hh, ww, 8).transpose(1, 2, 0, 3).reshape(hh, ww, cc)
+                d = np.abs(got - ref)
+                layers[nm] = {"equal_frac": float((d == 0).mean()), "maxabs": float(d.max()), "max_ref": float(np.abs(ref).max())}
+            pd = e.dbg_read("convPD").reshape(H // 8, Wd // 8, 512)
+            refp = np.concatenate([keepq["convPa"][0].permute(1, 2, 0).numpy(), keepq["convDa"][0].permute(1, 2, 0).numpy()], 2)
+            d = np.abs(pd - refp)
+            layers["convPa|Da"] = {"equal_frac": float((d == 0).mean()), "maxabs": float(d.max()), "max_ref": float(np.abs(refp).max())}
+            lg_ = e.dbg_read("logits").reshape(H // 8, Wd // 8, 80)[:, :, :65]
+            refl = keepq["logits"][0].permute(1, 2, 0).numpy()
+            layers["logits"] = {"maxabs": float(np.abs(lg_ - refl).max()), "max_ref": float(np.abs(refl).max()),
+                                "vs_fp32_maxabs": None}
+            out[name]["layers_vs_quant"] = layers
         comm = {tuple(k): i for i, k in enumerate(oq["kpts"])}
         idx = [(comm[tuple(k)], j) for j, k in enumerate(r["kpts"]) if tuple(k) in comm]
         io, ig = np.array(idx).T
