@@ -137,17 +137,4 @@ int plan_stem_conv(StemPlan* pl, const __half* img16, int n_cap, const __half* w
 int launch_stem_conv(const StemPlan& pl, int n_img, cudaStream_t st);
 int stem_conv_init();
 
-// ---- fused LightGlue FFN block (lg_ffn.cu) ---------------------------------------------------------------------------
-struct FfnPlan {
-  CUtensorMap tmX, tmW0, tmW3;
-  const float *b0 = nullptr, *ln_g = nullptr, *ln_b = nullptr, *b3 = nullptr;
-  float* x32 = nullptr;
-  __half* x16 = nullptr;
-  int ld16 = 0, T_cap = 0;
-};
-int lg_ffn_init();
-int plan_lg_ffn(FfnPlan* pl, const __half* X2, int T_cap, const __half* W0, const __half* W3, const float* b0,
-                const float* ln_g, const float* ln_b, const float* b3, float* x32, __half* x16, int ld16);
-int launch_lg_ffn(const FfnPlan& pl, int T, cudaStream_t st);
-
 }  // namespace dv

@@ -34,14 +34,16 @@ struct LgLayer {
   float *bqkv, *bout, *bf0, *bf3, *bcqkv, *bcout, *bcf0, *bcf3;
   float *ln_g, *ln_b, *cln_g, *cln_b;
   GemmPlan p_qkv, p_out, p_f0, p_f3, pc_qkv, pc_out, pc_f0, pc_f3;
-  FfnPlan ffn_s, ffn_c;     // fused FFN blocks (lg_ffn.cu)
 };
 
 struct LgNet {
   int P = 1, segcap = 1024, Tcap = 0;
   int ln_grid = 148 * 8;               // grid-stride LayerNorm+GELU kernel: 8 CTAs of 8 warps per SM
-  bool fused_ffn = false;              // DV_LG_FUSED_FFN=1: single-kernel FFN (lg_ffn.cu; correct, but weight re-streaming
-                                       // per 128-row block makes it no faster than the 3-kernel path yet - r01 notes)
+  // out_proj folded into the FFN's first linear (DV_LG_FOLD_OUT=0 keeps the separate GEMM, A/B):
+  //   ffn.0([x | out_proj(ctx)]) = W0a x + (W0b Wout) ctx + (b0 + W0b bout)
+  // two linear maps with nothing in between compose offline (like folding BatchNorm into a convolution), so the
+  // attention writes its context straight into the second half of X2 and one GEMM launch per block disappears.
+  bool fold_out = true;
   float* Wr = nullptr;                 // [32,2]
   LgLayer L[LG_LAYERS];
   __half* wfinal = nullptr; float* bfinal = nullptr;   // pre-scaled by 256^-1/4
@@ -601,6 +603,27 @@ __global__ void __launch_bounds__(1024) k_lg_extract(const PairDesc* __restrict_
 // ------------------------------------------------------------------------------------------------ host
 namespace {
 
+// [W0a | W0b] (512 x 512), Wout (256 x 256)  ->  [W0a | W0b Wout], b0 + W0b bout.  fp64 accumulation so the fp16
+// rounding of the folded weights is reproducible by the oracle (oracle/quant.py does the same product in float64).
+void fold_out_proj(const std::vector<float>& w0, const std::vector<float>& b0, const std::vector<float>& wout,
+                   const std::vector<float>& bout, std::vector<float>* wf, std::vector<float>* bf) {
+  wf->assign(w0.begin(), w0.end());
+  bf->assign(b0.begin(), b0.end());
+  std::vector<double> acc(256);
+  for (int o = 0; o < 512; ++o) {
+    std::fill(acc.begin(), acc.end(), 0.0);
+    double bacc = (double)b0[o];
+    for (int m = 0; m < 256; ++m) {
+      const double wv = (double)w0[(size_t)o * 512 + 256 + m];
+      const float* wr = &wout[(size_t)m * 256];
+      for (int c = 0; c < 256; ++c) acc[c] += wv * (double)wr[c];
+      bacc += wv * (double)bout[m];
+    }
+    for (int c = 0; c < 256; ++c) (*wf)[(size_t)o * 512 + 256 + c] = (float)acc[c];
+    (*bf)[o] = (float)bacc;
+  }
+}
+
 int get_lin(Engine* e, const std::string& name, int cout, int cin, const HostTensor** w, const HostTensor** b) {
   *w = e->weight("lg." + name + ".weight");
   *b = e->weight("lg." + name + ".bias");
@@ -619,9 +642,8 @@ int lg_init(Engine* e) {
   g->P = e->B;
   g->segcap = (e->cfg.lg_max_kpts + 127) & ~127;
   g->Tcap = g->P * 2 * g->segcap;
-  { const char* env = getenv("DV_LG_FUSED_FFN"); g->fused_ffn = (env && env[0] == '1'); }
+  { const char* env = getenv("DV_LG_FOLD_OUT"); g->fold_out = !(env && env[0] == '0'); }
   DV_CUDA_OK(cudaFuncSetAttribute(k_lg_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-  DV_TRY(lg_ffn_init());
   const int T = g->Tcap, P = g->P, SC = g->segcap;
   {
     const HostTensor* wr = e->weight("lg.posenc.Wr.weight");
@@ -691,10 +713,17 @@ int lg_init(Engine* e) {
           }
       DV_TRY(e->upload_f16(wp, &L.wqkv)); DV_TRY(e->upload_f32(bp, &L.bqkv));
     }
-    DV_TRY(get_lin(e, ps + "out_proj", 256, 256, &w, &b));
-    DV_TRY(e->upload_f16(w->data, &L.wout)); DV_TRY(e->upload_f32(b->data, &L.bout));
+    const HostTensor *wo, *bo;
+    DV_TRY(get_lin(e, ps + "out_proj", 256, 256, &wo, &bo));
+    DV_TRY(e->upload_f16(wo->data, &L.wout)); DV_TRY(e->upload_f32(bo->data, &L.bout));
     DV_TRY(get_lin(e, ps + "ffn.0", 512, 512, &w, &b));
-    DV_TRY(e->upload_f16(w->data, &L.wf0)); DV_TRY(e->upload_f32(b->data, &L.bf0));
+    if (g->fold_out) {
+      std::vector<float> wf, bf;
+      fold_out_proj(w->data, b->data, wo->data, bo->data, &wf, &bf);
+      DV_TRY(e->upload_f16(wf, &L.wf0)); DV_TRY(e->upload_f32(bf, &L.bf0));
+    } else {
+      DV_TRY(e->upload_f16(w->data, &L.wf0)); DV_TRY(e->upload_f32(b->data, &L.bf0));
+    }
     DV_TRY(get_lin(e, ps + "ffn.3", 256, 512, &w, &b));
     DV_TRY(e->upload_f16(w->data, &L.wf3)); DV_TRY(e->upload_f32(b->data, &L.bf3));
     const HostTensor *lg_ = e->weight("lg." + ps + "ffn.1.weight"), *lb_ = e->weight("lg." + ps + "ffn.1.bias");
@@ -711,10 +740,16 @@ int lg_init(Engine* e) {
       bp.insert(bp.end(), bv->data.begin(), bv->data.end());
       DV_TRY(e->upload_f16(wp, &L.cqkv)); DV_TRY(e->upload_f32(bp, &L.bcqkv));
     }
-    DV_TRY(get_lin(e, pc + "to_out", 256, 256, &w, &b));
-    DV_TRY(e->upload_f16(w->data, &L.cout)); DV_TRY(e->upload_f32(b->data, &L.bcout));
+    DV_TRY(get_lin(e, pc + "to_out", 256, 256, &wo, &bo));
+    DV_TRY(e->upload_f16(wo->data, &L.cout)); DV_TRY(e->upload_f32(bo->data, &L.bcout));
     DV_TRY(get_lin(e, pc + "ffn.0", 512, 512, &w, &b));
-    DV_TRY(e->upload_f16(w->data, &L.cf0)); DV_TRY(e->upload_f32(b->data, &L.bcf0));
+    if (g->fold_out) {
+      std::vector<float> wf, bf;
+      fold_out_proj(w->data, b->data, wo->data, bo->data, &wf, &bf);
+      DV_TRY(e->upload_f16(wf, &L.cf0)); DV_TRY(e->upload_f32(bf, &L.bcf0));
+    } else {
+      DV_TRY(e->upload_f16(w->data, &L.cf0)); DV_TRY(e->upload_f32(b->data, &L.bcf0));
+    }
     DV_TRY(get_lin(e, pc + "ffn.3", 256, 512, &w, &b));
     DV_TRY(e->upload_f16(w->data, &L.cf3)); DV_TRY(e->upload_f32(b->data, &L.bcf3));
     // plans (A operands are fixed buffers; rows are set at launch)
@@ -725,8 +760,6 @@ int lg_init(Engine* e) {
     DV_TRY(plan_gemm(&L.p_f0, g->X2, 512, T, L.wf0, 512, 512, 512, ep16(g->ffh, 512, L.bf0)));
     { EpiParams ep; ep.out32 = g->x32; ep.ld32 = 256; ep.res32 = g->x32; ep.ldr32 = 256; ep.out16 = g->X2; ep.ld16 = 512; ep.bias = L.bf3;
       DV_TRY(plan_gemm(&L.p_f3, g->ffg, 512, T, L.wf3, 512, 256, 512, ep)); }
-    DV_TRY(plan_lg_ffn(&L.ffn_s, g->X2, T, L.wf0, L.wf3, L.bf0, L.ln_g, L.ln_b, L.bf3, g->x32, g->X2, 512));
-    DV_TRY(plan_lg_ffn(&L.ffn_c, g->X2, T, L.cf0, L.cf3, L.bcf0, L.cln_g, L.cln_b, L.bcf3, g->x32, g->X2, 512));
     DV_TRY(plan_gemm(&L.pc_qkv, g->X2, 512, T, L.cqkv, 256, 512, 256, ep16(g->qkv, 768, L.bcqkv)));
     DV_TRY(plan_gemm(&L.pc_out, g->ctx, 256, T, L.cout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bcout)));
     DV_TRY(plan_gemm(&L.pc_f0, g->X2, 512, T, L.cf0, 512, 512, 512, ep16(g->ffh, 512, L.bcf0)));
@@ -794,6 +827,9 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
   LgSeg* d_segs = g->d_segs + 2 * out_base;
   AttnJob *d_js = g->jobs_self + 2 * out_base, *d_jc = g->jobs_cross + 2 * out_base;
   AttnJobU *d_us = g->ju_self + 2 * out_base, *d_uc = g->ju_cross + 2 * out_base;
+  // attention output: the ctx buffer (separate out_proj GEMM), or - out_proj folded - the msg half of X2
+  __half* const octx = g->fold_out ? g->X2 + 256 : g->ctx;
+  const int oldo = g->fold_out ? 512 : 256;
   int off = 0, max_n_any = 0, max_m = 0, max_n = 0;
   for (int i = 0; i < 2 * P; ++i) {
     hs[i] = segs_in[i];
@@ -811,13 +847,13 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     for (int k = 0; k < 2; ++k) {
       const LgSeg& s = hs[2 * p + k];
       __half* base = g->qkv + (int64_t)s.off * 768;
-      hj[2 * p + k] = {base, base + 256, base + 512, g->ctx + (int64_t)s.off * 256, s.n, s.n, 768, 768, 768, 256};
+      hj[2 * p + k] = {base, base + 256, base + 512, octx + (int64_t)s.off * oldo, s.n, s.n, 768, 768, 768, oldo};
       hu[2 * p + k] = {s.off, s.n, s.off, s.n, 0, 256, 512, 0};
     }
     __half* b0 = g->qkv + (int64_t)s0.off * 768;
     __half* b1 = g->qkv + (int64_t)s1.off * 768;
-    hj[2 * g->P + 2 * p] = {b0, b1, b1 + 256, g->ctx + (int64_t)s0.off * 256, s0.n, s1.n, 768, 768, 768, 256};
-    hj[2 * g->P + 2 * p + 1] = {b1, b0, b0 + 256, g->ctx + (int64_t)s1.off * 256, s1.n, s0.n, 768, 768, 768, 256};
+    hj[2 * g->P + 2 * p] = {b0, b1, b1 + 256, octx + (int64_t)s0.off * oldo, s0.n, s1.n, 768, 768, 768, oldo};
+    hj[2 * g->P + 2 * p + 1] = {b1, b0, b0 + 256, octx + (int64_t)s1.off * oldo, s1.n, s0.n, 768, 768, 768, oldo};
     hu[2 * g->P + 2 * p] = {s0.off, s0.n, s1.off, s1.n, 0, 0, 256, 0};          // cross: qk of the other image, its v
     hu[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
   }
@@ -842,31 +878,23 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       DV_TRY(launch_gemm(L.p_qkv, T, e->st));
       if (!gemm_is_persistent())
         k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
-      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_js, 0.125f));
-      DV_TRY(launch_gemm(L.p_out, T, e->st));
-      if (g->fused_ffn) {
-        DV_TRY(launch_lg_ffn(L.ffn_s, T, e->st));
-      } else {
-        DV_TRY(launch_gemm(L.p_f0, T, e->st));
-        DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
-                              (const float*)L.ln_b, g->ffg, (int64_t)T));
-        DV_TRY(launch_gemm(L.p_f3, T, e->st));
-      }
+      if (!g->fold_out) DV_TRY(launch_gemm(L.p_out, T, e->st));
+      DV_TRY(launch_gemm(L.p_f0, T, e->st));
+      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
+                            (const float*)L.ln_b, g->ffg, (int64_t)T));
+      DV_TRY(launch_gemm(L.p_f3, T, e->st));
       // cross block
       DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
-      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, g->ctx, 0.125f, e->st));
+      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_jc, 0.125f));
-      DV_TRY(launch_gemm(L.pc_out, T, e->st));
-      if (g->fused_ffn) {
-        DV_TRY(launch_lg_ffn(L.ffn_c, T, e->st));
-      } else {
-        DV_TRY(launch_gemm(L.pc_f0, T, e->st));
-        DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
-                              (const float*)L.cln_b, g->ffg, (int64_t)T));
-        DV_TRY(launch_gemm(L.pc_f3, T, e->st));
-      }
-      DV_LAUNCHED(e, 13);
+      if (!g->fold_out) DV_TRY(launch_gemm(L.pc_out, T, e->st));
+      DV_TRY(launch_gemm(L.pc_f0, T, e->st));
+      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
+                            (const float*)L.cln_b, g->ffg, (int64_t)T));
+      DV_TRY(launch_gemm(L.pc_f3, T, e->st));
+      DV_LAUNCHED(e, g->fold_out ? 10 : 12);
     }
     DV_CUDA_OK(cudaGetLastError());
     DV_TRY(launch_gemm(g->p_final, T, e->st));

@@ -36,6 +36,7 @@ int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float*
 namespace dv {
 int lg_attn_init();
 int plan_lg_attn(CUtensorMap* tm, const __half* qkv, int T_cap);
-int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, float scale,
+// ctx: output base, row stride ldo halves (256 = the ctx buffer; 512 = straight into the msg half of X2)
+int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, int ldo, float scale,
                    cudaStream_t st);
 }  // namespace dv

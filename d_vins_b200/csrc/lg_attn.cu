@@ -50,7 +50,7 @@ __device__ __forceinline__ float ex2_approx(float x) {     // one MUFU op (exp2f
 template <bool LAZY>
 __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                               const AttnJobU* __restrict__ jobs,
-                                                              __half* __restrict__ ctx, float sl2, long long* dbg) {
+                                                              __half* __restrict__ ctx, int ldo, float sl2, long long* dbg) {
   const AttnJobU jb = jobs[blockIdx.z];
   const int q0 = blockIdx.x * 128;
   if (q0 >= jb.nq) return;                     // uniform per CTA
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
     }
     if (q0 + row < jb.nq) {
       const float inv = 1.f / l_run;
-      __half* op = ctx + (int64_t)(jb.q_row + q0 + row) * 256 + head * 64;
+      __half* op = ctx + (int64_t)(jb.q_row + q0 + row) * ldo + head * 64;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         __align__(16) __half2 hv[4];
@@ -317,7 +317,7 @@ int plan_lg_attn(CUtensorMap* tm, const __half* qkv, int T_cap) {
   return tmap_encode_f16(tm, qkv, 2, dims, strides, box, true);
 }
 
-int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, float scale,
+int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, int ldo, float scale,
                    cudaStream_t st) {
   if (n_jobs <= 0) return DV_OK;
   const dim3 grid(cdiv(max_nq, 128), 4, n_jobs);
@@ -327,9 +327,9 @@ int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int 
   if (want && !d_dbg) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
   static const bool lazy = [] { const char* e = getenv("DV_ATTN_LAZY"); return !(e && e[0] == '0'); }();   // A/B switch
   if (lazy)
-    lg_attn_umma_kernel<true><<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
+    lg_attn_umma_kernel<true><<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, ldo, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
   else
-    lg_attn_umma_kernel<false><<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
+    lg_attn_umma_kernel<false><<<grid, 192, SMEM_BYTES, st>>>(tm, jobs, ctx, ldo, scale * 1.4426950408889634f, want ? d_dbg : nullptr);
   DV_CUDA_OK(cudaGetLastError());
   if (want && ++calls == 18) {
     long long h[8];

@@ -16,6 +16,8 @@ Rounding points mirror the engine (d_vins_b200/csrc):
     stored fp16 after the rotary (rotary table itself stored as fp16 cos/sin); attention probabilities rounded to fp16
     before P.V while the row sum uses the unrounded values; ctx / msg / FFN hidden / GELU output stored fp16;
     final_proj weights pre-scaled by 1/4 and rounded to fp16, md stored fp16; similarity, log-softmax, matchability fp32.
+    out_proj / to_out are composed with the first FFN linear offline (W0b Wout in float64, then ONE fp16 rounding), so the
+    attention context feeds the FFN directly (lg.cu fold_out_proj).
 """
 from __future__ import annotations
 
@@ -123,8 +125,20 @@ def _attend(q16, k16, v16, scale):
     return h16(o / p.sum(dim=-1, keepdim=True))
 
 
-def _ffn_q(w, p, x32, x16, msg16):
-    h = h16(_lin16(w, p + "ffn.0", torch.cat([x16, msg16], -1)))
+def _folded_ffn0(w, p, out_name):
+    """[W0a | W0b Wout], b0 + W0b bout in float64 (lg.cu fold_out_proj), then the engine's fp16 weight rounding."""
+    W0 = w[p + "ffn.0.weight"].astype(np.float64); b0 = w[p + "ffn.0.bias"].astype(np.float64)
+    Wo = w[p + out_name + ".weight"].astype(np.float64); bo = w[p + out_name + ".bias"].astype(np.float64)
+    Wf = np.concatenate([W0[:, :256], W0[:, 256:] @ Wo], 1).astype(np.float32)
+    bf = (b0 + W0[:, 256:] @ bo).astype(np.float32)
+    return h16(torch.from_numpy(Wf)), torch.from_numpy(bf)
+
+
+def _ffn_q(w, p, x32, x16, msg16, folded=None):
+    if folded is not None:          # msg16 is the attention context; out_proj lives inside the folded weights
+        h = h16(F.linear(torch.cat([x16, msg16], -1), folded[0], folded[1]))
+    else:
+        h = h16(_lin16(w, p + "ffn.0", torch.cat([x16, msg16], -1)))
     h = F.layer_norm(h, (h.shape[-1],), _b(w, p + "ffn.1.weight"), _b(w, p + "ffn.1.bias"), eps=1e-5)
     g = h16(F.gelu(h))
     x32 = (F.linear(g, _w16(w, p + "ffn.3.weight")) + _b(w, p + "ffn.3.bias")) + x32
@@ -135,7 +149,7 @@ def _heads(t):
     return t.unflatten(-1, (olg.HEADS, -1)).transpose(0, 1)
 
 
-def self_block_q(w, i, x32, x16, enc16):
+def self_block_q(w, i, x32, x16, enc16, fold_out=True):
     p = "transformers.%d.self_attn." % i
     n = x16.shape[0]
     qkv = _lin16(w, p + "Wqkv", x16).unflatten(-1, (olg.HEADS, -1, 3)).transpose(0, 1)   # [h,n,64,3] fp32
@@ -148,24 +162,30 @@ def self_block_q(w, i, x32, x16, enc16):
         return torch.stack((x0 * c[None] - x1 * s[None], x1 * c[None] + x0 * s[None]), dim=-1).flatten(start_dim=-2)
     q16, k16, v16 = h16(rope(q)), h16(rope(k)), h16(v)
     ctx16 = _attend(q16, k16, v16, 0.125).transpose(0, 1).reshape(n, -1)
+    if fold_out:
+        return _ffn_q(w, p, x32, x16, ctx16, _folded_ffn0(w, p, "out_proj"))
     msg16 = h16(_lin16(w, p + "out_proj", ctx16))
     return _ffn_q(w, p, x32, x16, msg16)
 
 
-def cross_block_q(w, i, x0, x1):
+def cross_block_q(w, i, x0, x1, fold_out=True):
     p = "transformers.%d.cross_attn." % i
     (x0_32, x0_16), (x1_32, x1_16) = x0, x1
     qk0, qk1 = _heads(h16(_lin16(w, p + "to_qk", x0_16))), _heads(h16(_lin16(w, p + "to_qk", x1_16)))
     v0, v1 = _heads(h16(_lin16(w, p + "to_v", x0_16))), _heads(h16(_lin16(w, p + "to_v", x1_16)))
     m0 = _attend(qk0, qk1, v1, 0.125).transpose(0, 1).reshape(x0_16.shape[0], -1)
     m1 = _attend(qk1, qk0, v0, 0.125).transpose(0, 1).reshape(x1_16.shape[0], -1)
+    if fold_out:
+        fw = _folded_ffn0(w, p, "to_out")
+        return _ffn_q(w, p, x0_32, x0_16, m0, fw), _ffn_q(w, p, x1_32, x1_16, m1, fw)
     m0 = h16(_lin16(w, p + "to_out", m0))
     m1 = h16(_lin16(w, p + "to_out", m1))
     return _ffn_q(w, p, x0_32, x0_16, m0), _ffn_q(w, p, x1_32, x1_16, m1)
 
 
-def lightglue_q(w, kpts0, kpts1, desc0, desc1, h0, w0, h1, w1, keep=None):
-    """oracle.lightglue.lightglue with the engine's operand precisions (see module docstring)."""
+def lightglue_q(w, kpts0, kpts1, desc0, desc1, h0, w0, h1, w1, keep=None, fold_out=True):
+    """oracle.lightglue.lightglue with the engine's operand precisions (see module docstring).  fold_out mirrors the
+    engine default (DV_LG_FOLD_OUT): out_proj / to_out composed with the FFN's first linear before the fp16 rounding."""
     k0 = torch.from_numpy(olg.normalize_kpts(np.asarray(kpts0, np.float32), w0, h0))
     k1 = torch.from_numpy(olg.normalize_kpts(np.asarray(kpts1, np.float32), w1, h1))
     x0 = torch.from_numpy(np.ascontiguousarray(desc0, dtype=np.float32))
@@ -177,9 +197,9 @@ def lightglue_q(w, kpts0, kpts1, desc0, desc1, h0, w0, h1, w1, keep=None):
         e0, e1 = enc16(k0), enc16(k1)
         x0, x1 = (x0, h16(x0)), (x1, h16(x1))
         for i in range(olg.N_LAYERS):
-            x0 = self_block_q(w, i, x0[0], x0[1], e0)
-            x1 = self_block_q(w, i, x1[0], x1[1], e1)
-            x0, x1 = cross_block_q(w, i, x0, x1)
+            x0 = self_block_q(w, i, x0[0], x0[1], e0, fold_out)
+            x1 = self_block_q(w, i, x1[0], x1[1], e1, fold_out)
+            x0, x1 = cross_block_q(w, i, x0, x1, fold_out)
         p = "log_assignment.%d." % (olg.N_LAYERS - 1)
         md0 = h16(_lin16(w, p + "final_proj", x0[1], scale=0.25))
         md1 = h16(_lin16(w, p + "final_proj", x1[1], scale=0.25))

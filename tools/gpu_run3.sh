@@ -19,6 +19,7 @@ run mix32 DV_MIX_CHUNK=32
 run lg16 DV_LG_CHUNK=16
 run lg32 DV_LG_CHUNK=32
 run knn0 DV_KNN_FUSED=0
+run nofold DV_LG_FOLD_OUT=0
 timeout 300 python bench.py --config mix_knn_10k --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_mix_knn_10k.json 2> gpurun_out/bench_mix_knn_10k.err; python -c "
 import json; d=json.load(open('gpurun_out/bench_mix_knn_10k.json')); print('mixknn', round(d['value']), d['roofline']['achieved'], d['roofline']['avg_launch_ms'], d['stage_ms_per_round'])"
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_euroc.json 2> gpurun_out/bench_euroc.err; python -c "
