@@ -84,6 +84,10 @@ int launch_gemm_staged(const GemmPlan& pl, const GemmParams& p, long m_tiles, cu
 bool gemm_wres_eligible(const GemmPlan& pl, long m_tiles);
 int gemm_wres_init();
 int launch_gemm_wres(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
+// the same on CTA pairs (gemm_pair.cu, cta_group::2): a pair shares a 256-column slab, M = 256 / N = 256 MMAs
+bool gemm_pair_eligible(const GemmPlan& pl, long m_tiles);
+int gemm_pair_init();
+int launch_gemm_pair(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
 
 // ---- weights-stationary halo-tile 3x3 convolution, 64 -> 64 channels (conv_halo.cu) -------------------------------
 // Activations in the channel-blocked layout [N][C/8][H][W][8] ("NC/8HWC8"): one TMA box per 16x8-pixel output tile

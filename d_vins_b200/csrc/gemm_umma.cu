@@ -260,6 +260,8 @@ int gemm_init() {
   if (rc) return rc;
   rc = gemm_wres_init();
   if (rc) return rc;
+  rc = gemm_pair_init();
+  if (rc) return rc;
   rc = conv_halo128_init();
   if (rc) return rc;
   rc = stem_conv_init();
@@ -296,8 +298,8 @@ int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t*
 int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long cols, long rows, long pitch_bytes,
                      int box_cols, int box_rows) {
   if (!g_encode || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0 ||
-      box_cols * elem_bytes != 128) {
-    set_error("tmap_encode_rows: base / pitch must be 16-byte aligned and the box 128 bytes wide");
+      (box_cols * elem_bytes != 128 && box_cols * elem_bytes != 64)) {
+    set_error("tmap_encode_rows: base / pitch must be 16-byte aligned and the box 128 or 64 bytes wide");
     return DV_ERR_INVALID;
   }
   cuuint64_t d[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -306,7 +308,8 @@ int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long col
   cuuint32_t es[2] = {1, 1};
   CUresult r = g_encode(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        box_cols * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char b[256];
@@ -429,20 +432,23 @@ int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st) {
   if (want_time && !p.conv) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const bool pair = pl.staged && gemm_pair_eligible(pl, m_tiles);
     const bool wres = pl.staged && gemm_wres_eligible(pl, m_tiles);
     cudaEventRecord(e0, st);
-    int rc = wres ? launch_gemm_wres(pl, p, m_tiles, st)
-                  : (pl.staged ? launch_gemm_staged(pl, p, m_tiles, st) : launch_gemm_persistent(pl, p, m_tiles, st));
+    int rc = pair ? launch_gemm_pair(pl, p, m_tiles, st)
+             : wres ? launch_gemm_wres(pl, p, m_tiles, st)
+                    : (pl.staged ? launch_gemm_staged(pl, p, m_tiles, st) : launch_gemm_persistent(pl, p, m_tiles, st));
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     fprintf(stderr, "[gemm time] M %d N %d K %d %s: %.1f us = %.0f TFLOP/s\n", p.M, p.N, p.K,
-            wres ? "wres" : (pl.staged ? "staged" : "persist"), ms * 1e3, 2.0 * p.M * p.N * p.K / (ms * 1e-3) / 1e12);
+            pair ? "pair" : wres ? "wres" : (pl.staged ? "staged" : "persist"), ms * 1e3, 2.0 * p.M * p.N * p.K / (ms * 1e-3) / 1e12);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
   }
   if (pl.staged) {
+    if (gemm_pair_eligible(pl, m_tiles)) return launch_gemm_pair(pl, p, m_tiles, st);
     if (gemm_wres_eligible(pl, m_tiles)) return launch_gemm_wres(pl, p, m_tiles, st);
     return launch_gemm_staged(pl, p, m_tiles, st);
   }

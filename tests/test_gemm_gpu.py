@@ -100,7 +100,10 @@ def test_conv3x3_halo128(eng, n, h, w, cin, cout, pool, blocked):
                                    (129, 136, 128), (4099, 1024, 320),
                                    # weights-resident kernel (gemm_wres.cu): 256-column slabs (K <= 256), 128-column
                                    # slabs (K = 512), several row tiles per CTA, ragged last tile
-                                   (2000, 768, 256), (20001, 256, 256), (1500, 512, 512), (2085, 1024, 128)])
+                                   (2000, 768, 256), (20001, 256, 256), (1500, 512, 512), (2085, 1024, 128),
+                                   # CTA-pair kernel (gemm_pair.cu, cta_group::2): 256-row super-tiles, ragged M that ends
+                                   # in the first / second CTA's half, one and several slabs, K = 512 (three A stages)
+                                   (4000, 512, 512), (5249, 256, 512), (33010, 768, 256), (2048, 256, 64)])
 @pytest.mark.parametrize("mode", ["o16", "o32", "res32_o32_o16", "res16_relu_o16", "res32_o16"])
 def test_gemm_fused_epilogues(eng, M, N, K, mode):
     """Every epilogue operand of the staged (TMA in / TMA out) kernel: fp16 / fp32 outputs, in-place fp32 residual,
