@@ -538,6 +538,8 @@ def main():
     # ---------------- (2) end to end through the C ABI: pinned host frames in, results out, every step
     one_step(upload=True)
     h2d[0] = d2h[0] = 0
+    for k in partner:
+        partner[k] = 0
     barrier()
     eng.timer_start()
     for _ in range(args.steps):
@@ -545,6 +547,7 @@ def main():
     ms_e2e = eng.timer_stop()
     barrier()
     ms_e2e = max_over_ranks(ms_e2e)
+    partner_e2e = dict(partner)          # new content every round: at N > 1 the kNN-retrieved keyframe lives on a peer
     h2d_step, d2h_step = h2d[0] // args.steps, d2h[0] // args.steps
     # ---------------- (3) the device-resident loop once more: separates the cost of the uploads from clock / power
     # drift between the two timed regions (the e2e loop runs on a GPU that has been at full load for longer)
@@ -674,6 +677,7 @@ def main():
         "gpu_launches": int(launches),
         "p50_match_ms": p50,
         "lg_partner_counts_rank0": partner_dev,
+        "lg_partner_counts_e2e_rank0": partner_e2e,
         "bank_rows_end": eng.bank_size(),
         "stage_ms_per_round": stage_ms,
         "roofline": roofline,

@@ -69,6 +69,10 @@ struct LgNet {
   // per-call tables
   AttnJob *jobs_self = nullptr, *jobs_cross = nullptr, *h_jobs = nullptr;   // device x2, pinned host [4P]
   AttnJobU *ju_self = nullptr, *ju_cross = nullptr, *h_ju = nullptr;        // tcgen05 attention job tables
+  // persistent attention: cost-sorted (job, head, query tile) lists, self then cross, 64 entries per pair slot each
+  int *it_self = nullptr, *it_cross = nullptr, *h_items = nullptr;
+  bool attn_persist = true;            // DV_ATTN_PERSIST=0: one CTA per tile (A/B)
+  int ipp = 64;                        // item-list entries per pair slot
   CUtensorMap tm_qkv;
   bool attn_umma = true;               // tcgen05 attention (lg_attn.cu: MN-major V operand, O accumulated in TMEM with lazy
                                        // rescale, two CTAs per SM); DV_LG_ATTN=mma: the mma.sync flash kernel of this file
@@ -681,6 +685,12 @@ int lg_init(Engine* e) {
   DV_TRY(e->alloc(&g->ju_self, (size_t)2 * P));
   DV_TRY(e->alloc(&g->ju_cross, (size_t)2 * P));
   DV_TRY(e->alloc_pinned(&g->h_ju, (size_t)4 * P));
+  { const char* env = getenv("DV_ATTN_PERSIST"); g->attn_persist = !(env && env[0] == '0'); }
+  g->ipp = 8 * (g->segcap / 128);      // 2 images x 4 heads x query tiles
+  if (g->segcap > 2048) g->attn_persist = false;          // item code: 4 bits of query tile
+  DV_TRY(e->alloc(&g->it_self, (size_t)g->ipp * P));
+  DV_TRY(e->alloc(&g->it_cross, (size_t)g->ipp * P));
+  DV_TRY(e->alloc_pinned(&g->h_items, (size_t)2 * g->ipp * P));
   // default: the tcgen05 attention (lg_attn.cu, lazy rescale, two CTAs per SM); DV_LG_ATTN=mma selects the mma.sync kernel
   { const char* env = getenv("DV_LG_ATTN"); g->attn_umma = !(env && env[0] == 'm'); }
   DV_TRY(lg_attn_init());
@@ -827,6 +837,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
   LgSeg* d_segs = g->d_segs + 2 * out_base;
   AttnJob *d_js = g->jobs_self + 2 * out_base, *d_jc = g->jobs_cross + 2 * out_base;
   AttnJobU *d_us = g->ju_self + 2 * out_base, *d_uc = g->ju_cross + 2 * out_base;
+  int *hi_s = g->h_items + g->ipp * out_base, *hi_c = g->h_items + g->ipp * g->P + g->ipp * out_base;
+  int *d_is = g->it_self + g->ipp * out_base, *d_ic = g->it_cross + g->ipp * out_base;
   // attention output: the ctx buffer (separate out_proj GEMM), or - out_proj folded - the msg half of X2
   __half* const octx = g->fold_out ? g->X2 + 256 : g->ctx;
   const int oldo = g->fold_out ? 512 : 256;
@@ -857,6 +869,11 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     hu[2 * g->P + 2 * p] = {s0.off, s0.n, s1.off, s1.n, 0, 0, 256, 0};          // cross: qk of the other image, its v
     hu[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
   }
+  int n_is = 0, n_ic = 0;
+  if (g->attn_umma && g->attn_persist) {
+    n_is = lg_attn_items(hu, 2 * P, hi_s);
+    n_ic = lg_attn_items(hu + 2 * g->P, 2 * P, hi_c);
+  }
   // Everything below only queues work on e->st; the per-call tables above sit in pinned memory at fixed addresses.  A
   // single pair (the per-keyframe latency path: ~130 launches of a few microseconds each) is captured once per (m, n)
   // into a CUDA graph and replayed; batched calls amortise their launches over the batch and stay eager.
@@ -868,6 +885,10 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     DV_CUDA_OK(cudaMemcpyAsync(d_jc, hj + 2 * g->P, sizeof(AttnJob) * 2 * P, cudaMemcpyHostToDevice, e->st));
     DV_CUDA_OK(cudaMemcpyAsync(d_us, hu, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
     DV_CUDA_OK(cudaMemcpyAsync(d_uc, hu + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
+    if (n_is) {
+      DV_CUDA_OK(cudaMemcpyAsync(d_is, hi_s, sizeof(int) * n_is, cudaMemcpyHostToDevice, e->st));
+      DV_CUDA_OK(cudaMemcpyAsync(d_ic, hi_c, sizeof(int) * n_ic, cudaMemcpyHostToDevice, e->st));
+    }
     k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
     DV_LAUNCHED(e, 1);
     if (after_load && *after_load) DV_TRY((*after_load)());
@@ -878,7 +899,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       DV_TRY(launch_gemm(L.p_qkv, T, e->st));
       if (!gemm_is_persistent())
         k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
-      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
+      if (n_is) DV_TRY(launch_lg_attn_persist(g->tm_qkv, d_us, d_is, n_is, octx, oldo, 0.125f, e->st));
+      else if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_js, 0.125f));
       if (!g->fold_out) DV_TRY(launch_gemm(L.p_out, T, e->st));
       DV_TRY(launch_gemm(L.p_f0, T, e->st));
@@ -887,7 +909,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       DV_TRY(launch_gemm(L.p_f3, T, e->st));
       // cross block
       DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
-      if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
+      if (n_ic) DV_TRY(launch_lg_attn_persist(g->tm_qkv, d_uc, d_ic, n_ic, octx, oldo, 0.125f, e->st));
+      else if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_jc, 0.125f));
       if (!g->fold_out) DV_TRY(launch_gemm(L.pc_out, T, e->st));
       DV_TRY(launch_gemm(L.pc_f0, T, e->st));

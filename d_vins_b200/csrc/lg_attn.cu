@@ -15,6 +15,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "gemm.h"
 #include "lg.h"
@@ -305,9 +308,301 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (default, r02).  ncu of the kernel above at batch 32 (profiles/r02_attention_ncu.txt): MUFU pipe 30 %
+// busy, tensor pipe 19 %, 5.2 waves of 3072 CTAs of which a third exit at once - the steady-state chunk loop is fine, the
+// time goes into per-CTA set-up (barrier init, TMEM allocation, first Q/K/V round trip), the O read-out / store tail and
+// the wave quantisation of CTAs whose work differs 4 x (150- vs 662-token images).  Here TWO resident CTAs per SM walk a
+// host-built list of (job, head, query tile) items, most expensive first, in snake order over the CTAs (round r: CTA b
+// takes item r*G + b, odd rounds G-1-b), so barriers / TMEM are set up once, the TMA warp prefetches the next item's
+// Q/K/V under the current item's tail, and the softmax warps of the SM's two CTAs always have work for the MUFU pipe.
+// All barriers run on global counters (items n, chunks g) instead of per-CTA indices; q_empty releases the Q tile.
+template <bool LAZY>
+__global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                 const AttnJobU* __restrict__ jobs,
+                                                                 const int* __restrict__ items, int n_items,
+                                                                 __half* __restrict__ ctx, int ldo, float sl2) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  if ((int)(smem - smem_raw) > ALIGN_SLACK) __trap();
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* kv_full = q_full + 1;              // [2]
+  uint64_t* kv_empty = kv_full + 2;            // [2]
+  uint64_t* s_full = kv_empty + 2;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* o_full = p_ready + 1;
+  uint64_t* q_empty = o_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (int)gridDim.x, bid = (int)blockIdx.x;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(q_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  // item of this CTA in round r (-1: none; then no later round has one either)
+  auto item_at = [&](int r) -> int {
+    const int idx = r * G + ((r & 1) ? G - 1 - bid : bid);
+    return idx < n_items ? __ldg(items + idx) : -1;
+  };
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int g = 0;
+      for (int n = 0;; ++n) {
+        const int it = item_at(n);
+        if (it < 0) break;
+        const AttnJobU jb = jobs[it >> 8];
+        const int head = (it >> 4) & 15, q0 = (it & 15) * 128;
+        const int n_chunks = (jb.nk + 127) >> 7;
+        if (n > 0) mbar_wait(q_empty, (n - 1) & 1);          // every S product of the previous item has read Q
+        mbar_arrive_expect_tx(q_full, TILE_BYTES);
+        tma_load_2d(smem + OFF_Q, &tmQKV, q_full, jb.q_col + head * 64, jb.q_row + q0);
+        for (int j = 0; j < n_chunks; ++j, ++g) {
+          const int s = g & 1;
+          mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_2d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &kv_full[s], jb.k_col + head * 64, jb.k_row + j * 128);
+          tma_load_2d(smem + OFF_V + s * TILE_BYTES, &tmQKV, &kv_full[s], jb.v_col + head * 64, jb.k_row + j * 128);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_s = make_idesc_f16_f32(128, 128);                 // A, B K-major
+      constexpr uint32_t idesc_pv = make_idesc_f16_f32(128, 64) | (1u << 16);    // B (= V) MN-major
+      const uint64_t dq = make_desc_sw128(smem_u32(smem + OFF_Q));
+      const uint64_t dp = make_desc_sw128(smem_u32(smem + OFF_P));
+      int g = 0;
+      for (int n = 0;; ++n) {
+        const int it = item_at(n);
+        if (it < 0) break;
+        const AttnJobU jb = jobs[it >> 8];
+        const int n_chunks = (jb.nk + 127) >> 7;
+        mbar_wait(q_full, n & 1);
+        for (int j = 0; j < n_chunks; ++j, ++g) {
+          const int s = g & 1;
+          mbar_wait(&kv_full[s], (g >> 1) & 1);
+          tc_fence_after();
+          const uint64_t dk = make_desc_sw128(smem_u32(smem + OFF_K + s * TILE_BYTES));
+          const uint64_t dv = make_desc_sw128(smem_u32(smem + OFF_V + s * TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                                             // head_dim 64 = 4 k-steps
+            tc_mma_f16(tmem_base, dq + (uint64_t)(k * 2), dk + (uint64_t)(k * 2), idesc_s, (uint32_t)(k != 0));
+          tc_commit(s_full);
+          if (j == n_chunks - 1) tc_commit(q_empty);
+          mbar_wait(p_ready, g & 1);
+          tc_fence_after();
+          const int pv_steps = min(8, (jb.nk - j * 128 + 15) >> 4);                // only the k-steps that hold valid keys
+          for (int k = 0; k < pv_steps; ++k)
+            tc_mma_f16(tmem_base + 128, dp + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
+                       dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)(LAZY ? (j | k) != 0 : k != 0));
+          tc_commit(o_full);
+          tc_commit(&kv_empty[s]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction: thread == query row
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* prow = smem + OFF_P + row * 128;
+    int g = 0;
+    for (int n = 0;; ++n) {
+      const int it = item_at(n);
+      if (it < 0) break;
+      const AttnJobU jb = jobs[it >> 8];
+      const int head = (it >> 4) & 15, q0 = (it & 15) * 128;
+      const int n_chunks = (jb.nk + 127) >> 7;
+      const bool warp_live = q0 + q * 32 < jb.nq;
+      float o[64];
+      if (!LAZY) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o[i] = 0.f;
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_chunks; ++j, ++g) {
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        const int kbase = j * 128;
+        const int ngrp = min(4, (jb.nk - kbase + 31) >> 5);    // 32-key groups holding valid keys (PV reads no further)
+        if (!warp_live) {                                      // every row of this warp is >= nq: nothing to compute
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cnt(p_ready);
+          if (!LAZY) mbar_wait(o_full, g & 1);
+          continue;
+        }
+        auto sweep = [&](float mb, float& sum, float& mx) {
+#pragma unroll 1
+          for (int c = 0; c < ngrp; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tl + c * 32, r);
+            tmem_ld_wait();
+            __align__(16) __half2 hv[16];
+            if (kbase + c * 32 + 32 <= jb.nk) {                 // full 32-key group (warp-uniform): no masking
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
+                mx = fmaxf(mx, fmaxf(s0, s1));
+                const float p0 = ex2_approx(fmaf(s0, sl2, -mb));
+                const float p1 = ex2_approx(fmaf(s1, sl2, -mb));
+                hv[i] = __floats2half2_rn(p0, p1);
+                sum += p0 + p1;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int key = kbase + c * 32 + 2 * i;
+                const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
+                if (key < jb.nk) mx = fmaxf(mx, s0);
+                if (key + 1 < jb.nk) mx = fmaxf(mx, s1);
+                const float p0 = key < jb.nk ? ex2_approx(fmaf(s0, sl2, -mb)) : 0.f;
+                const float p1 = key + 1 < jb.nk ? ex2_approx(fmaf(s1, sl2, -mb)) : 0.f;
+                hv[i] = __floats2half2_rn(p0, p1);
+                sum += p0 + p1;
+              }
+            }
+            uint8_t* tile = prow + (c >> 1) * TILE_BYTES;
+            const int ch0 = (c & 1) * 4;
+#pragma unroll
+            for (int gg = 0; gg < 4; ++gg)
+              *reinterpret_cast<uint4*>(tile + (((ch0 + gg) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[gg];
+          }
+        };
+        float corr = 1.f, sum = 0.f;
+        if (LAZY && j > 0) {
+          // PV(j-1) has retired (it precedes S(j) on the tensor pipe): the P tiles may be overwritten, O is stable.
+          mbar_wait(o_full, (g - 1) & 1);
+          tc_fence_after();
+          float mx = -INFINITY;
+          sweep(m_run * sl2, sum, mx);
+          const bool grow = (mx - m_run) * sl2 > 8.f;
+          if (__any_sync(0xffffffffu, grow)) {
+            if (grow) { corr = ex2_approx((m_run - mx) * sl2); m_run = mx; l_run *= corr; }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t r[32];
+              tmem_ld32(tl + 128 + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+              tmem_st32(tl + 128 + c * 32, r);
+            }
+            tmem_st_wait();
+            sum = 0.f;
+            float unused = -INFINITY;
+            sweep(m_run * sl2, sum, unused);
+          }
+        } else {
+          float mx = -INFINITY;
+#pragma unroll 1
+          for (int c = 0; c < ngrp; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tl + c * 32, r);
+            tmem_ld_wait();
+            if (kbase + c * 32 + 32 <= jb.nk) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+          }
+          if (LAZY) {
+            m_run = mx;                                         // first chunk: the reference is its own maximum
+          } else {
+            const float m_new = fmaxf(m_run, mx);               // finite: every chunk holds >= 1 valid key
+            corr = ex2_approx((m_run - m_new) * sl2);
+            m_run = m_new;
+            l_run *= corr;
+          }
+          float unused = -INFINITY;
+          sweep(m_run * sl2, sum, unused);
+        }
+        l_run += sum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cnt(p_ready);
+        if (!LAZY) {
+          if (__any_sync(0xffffffffu, corr != 1.f)) {          // the running maxima settle after the first chunks
+#pragma unroll
+            for (int i = 0; i < 64; ++i) o[i] *= corr;
+          }
+          mbar_wait(o_full, g & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tl + 128 + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
+          }
+          tc_fence_before();     // order these TMEM reads before the next chunk's MMAs (released through p_ready / s_full)
+        }
+      }
+      if (LAZY) {
+        // PV of the item's last chunk has retired: O is complete, and the P tiles / the O columns may be rewritten by the
+        // next item.  EVERY warp waits (a warp that idled through this item may be live in the next one).
+        mbar_wait(o_full, (g - 1) & 1);
+        tc_fence_after();
+        if (warp_live) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tl + 128 + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(r[i]);
+          }
+        }
+        tc_fence_before();
+      }
+      if (q0 + row < jb.nq) {
+        const float inv = 1.f / l_run;
+        __half* op = ctx + (int64_t)(jb.q_row + q0 + row) * ldo + head * 64;
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) {
+          __align__(16) __half2 hv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(o[gg * 8 + 2 * i] * inv, o[gg * 8 + 2 * i + 1] * inv);
+          reinterpret_cast<uint4*>(op)[gg] = *reinterpret_cast<const uint4*>(hv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int g_attn_sms = 148;
+
 int lg_attn_init() {
   DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  int dev = 0;
+  DV_CUDA_OK(cudaGetDevice(&dev));
+  DV_CUDA_OK(cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev));
   return DV_OK;
 }
 
@@ -339,6 +634,42 @@ int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int 
             h[5], h[0] / h[5], h[1] / h[5], h[2] / h[5], h[3] / h[5], h[4] / h[5]);
   }
   return DV_OK;
+}
+
+// Persistent launch: `items` = device list of (job << 8 | head << 4 | query tile), most expensive first (lg_attn_items).
+int launch_lg_attn_persist(const CUtensorMap& tm, const AttnJobU* jobs, const int* items, int n_items, __half* ctx, int ldo,
+                           float scale, cudaStream_t st) {
+  if (n_items <= 0) return DV_OK;
+  static const bool lazy = [] { const char* e = getenv("DV_ATTN_LAZY"); return !(e && e[0] == '0'); }();   // A/B switch
+  const int grid = n_items < 2 * g_attn_sms ? n_items : 2 * g_attn_sms;
+  if (lazy)
+    DV_CUDA_OK(launch_pdl(lg_attn_persist_kernel<true>, dim3(grid), dim3(192), (size_t)SMEM_BYTES, st, tm, jobs, items, n_items,
+                          ctx, ldo, scale * 1.4426950408889634f));
+  else
+    DV_CUDA_OK(launch_pdl(lg_attn_persist_kernel<false>, dim3(grid), dim3(192), (size_t)SMEM_BYTES, st, tm, jobs, items, n_items,
+                          ctx, ldo, scale * 1.4426950408889634f));
+  DV_CUDA_OK(cudaGetLastError());
+  return DV_OK;
+}
+
+// Host side of the item list: every (job, head, 128-query tile) of `jobs`, sorted by decreasing cost.  A tile occupies its
+// CTA for (32-key groups of the key side) sweeps whatever its number of live rows, so the key count ranks first and the
+// live 32-row warps (MUFU work) break ties.  Returns the number of items written (<= n_jobs * 4 * 8).
+int lg_attn_items(const AttnJobU* jobs, int n_jobs, int* items) {
+  struct It { int cost, code; };
+  static thread_local std::vector<It> tmp;
+  tmp.clear();
+  for (int jn = 0; jn < n_jobs; ++jn) {
+    const int groups = (jobs[jn].nk + 31) >> 5;
+    for (int qt = 0; qt * 128 < jobs[jn].nq; ++qt) {
+      const int rows = jobs[jn].nq - qt * 128 < 128 ? jobs[jn].nq - qt * 128 : 128;
+      const int cost = groups * 8 + ((rows + 31) >> 5);
+      for (int h = 0; h < 4; ++h) tmp.push_back({cost, (jn << 8) | (h << 4) | qt});
+    }
+  }
+  std::stable_sort(tmp.begin(), tmp.end(), [](const It& a, const It& b) { return a.cost > b.cost; });
+  for (size_t i = 0; i < tmp.size(); ++i) items[i] = tmp[i].code;
+  return (int)tmp.size();
 }
 
 }  // namespace dv

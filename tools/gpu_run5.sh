@@ -1,5 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-DV_GEMM_PAIR=1 DV_GEMM_PAIR_NARROW=2 timeout 600 python -m pytest tests/test_gemm_gpu.py -m gpu -x -q 2>&1 | tail -n 8
-timeout 600 python -m pytest tests/test_gemm_gpu.py tests/test_lightglue_gpu.py tests/test_parity_exact_gpu.py -m gpu -x -q 2>&1 | tail -n 8
+timeout 900 python -m pytest tests/test_lightglue_gpu.py tests/test_parity_exact_gpu.py tests/test_graph_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q 2>&1 | tail -n 8
 bash tools/gpu_run6.sh

@@ -8,7 +8,5 @@ try:
 except Exception as ex: print("$name FAILED", ex)
 PY
 }
-run pair0 DV_GEMM_PAIR=0
-run pair2n0 DV_GEMM_PAIR=2 DV_GEMM_PAIR_NARROW=0
-run pair2n1 DV_GEMM_PAIR=2 DV_GEMM_PAIR_NARROW=1
-run pair2n2 DV_GEMM_PAIR=2 DV_GEMM_PAIR_NARROW=2
+run persist0 DV_ATTN_PERSIST=0
+run persist1 DV_ATTN_PERSIST=1
