@@ -70,7 +70,7 @@ struct LgNet {
   AttnJob *jobs_self = nullptr, *jobs_cross = nullptr, *h_jobs = nullptr;   // device x2, pinned host [4P]
   AttnJobU *ju_self = nullptr, *ju_cross = nullptr, *h_ju = nullptr;        // tcgen05 attention job tables
   // persistent attention: cost-sorted (job, head, query tile) lists, self then cross, 64 entries per pair slot each
-  int *it_self = nullptr, *it_cross = nullptr, *h_items = nullptr;
+  uint8_t *it_self = nullptr, *it_cross = nullptr, *h_items = nullptr;   // 32-byte descriptors
   bool attn_persist = true;            // DV_ATTN_PERSIST=0: one CTA per tile (A/B)
   int ipp = 64;                        // item-list entries per pair slot
   CUtensorMap tm_qkv;
@@ -687,10 +687,10 @@ int lg_init(Engine* e) {
   DV_TRY(e->alloc_pinned(&g->h_ju, (size_t)4 * P));
   { const char* env = getenv("DV_ATTN_PERSIST"); g->attn_persist = !(env && env[0] == '0'); }
   g->ipp = 8 * (g->segcap / 128);      // 2 images x 4 heads x query tiles
-  if (g->segcap > 2048) g->attn_persist = false;          // item code: 4 bits of query tile
-  DV_TRY(e->alloc(&g->it_self, (size_t)g->ipp * P));
-  DV_TRY(e->alloc(&g->it_cross, (size_t)g->ipp * P));
-  DV_TRY(e->alloc_pinned(&g->h_items, (size_t)2 * g->ipp * P));
+  const size_t ib = (size_t)lg_attn_item_bytes();
+  DV_TRY(e->alloc(&g->it_self, ib * g->ipp * P));
+  DV_TRY(e->alloc(&g->it_cross, ib * g->ipp * P));
+  DV_TRY(e->alloc_pinned(&g->h_items, ib * 2 * g->ipp * P));
   // default: the tcgen05 attention (lg_attn.cu, lazy rescale, two CTAs per SM); DV_LG_ATTN=mma selects the mma.sync kernel
   { const char* env = getenv("DV_LG_ATTN"); g->attn_umma = !(env && env[0] == 'm'); }
   DV_TRY(lg_attn_init());
@@ -837,8 +837,9 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
   LgSeg* d_segs = g->d_segs + 2 * out_base;
   AttnJob *d_js = g->jobs_self + 2 * out_base, *d_jc = g->jobs_cross + 2 * out_base;
   AttnJobU *d_us = g->ju_self + 2 * out_base, *d_uc = g->ju_cross + 2 * out_base;
-  int *hi_s = g->h_items + g->ipp * out_base, *hi_c = g->h_items + g->ipp * g->P + g->ipp * out_base;
-  int *d_is = g->it_self + g->ipp * out_base, *d_ic = g->it_cross + g->ipp * out_base;
+  const size_t ib = (size_t)lg_attn_item_bytes();
+  uint8_t *hi_s = g->h_items + ib * g->ipp * out_base, *hi_c = g->h_items + ib * g->ipp * (g->P + out_base);
+  uint8_t *d_is = g->it_self + ib * g->ipp * out_base, *d_ic = g->it_cross + ib * g->ipp * out_base;
   // attention output: the ctx buffer (separate out_proj GEMM), or - out_proj folded - the msg half of X2
   __half* const octx = g->fold_out ? g->X2 + 256 : g->ctx;
   const int oldo = g->fold_out ? 512 : 256;
@@ -870,7 +871,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     hu[2 * g->P + 2 * p + 1] = {s1.off, s1.n, s0.off, s0.n, 0, 0, 256, 0};
   }
   int n_is = 0, n_ic = 0;
-  if (g->attn_umma && g->attn_persist) {
+  static const bool attn_lazy = [] { const char* en = getenv("DV_ATTN_LAZY"); return !(en && en[0] == '0'); }();
+  if (g->attn_umma && g->attn_persist && attn_lazy) {
     n_is = lg_attn_items(hu, 2 * P, hi_s);
     n_ic = lg_attn_items(hu + 2 * g->P, 2 * P, hi_c);
   }
@@ -886,8 +888,8 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     DV_CUDA_OK(cudaMemcpyAsync(d_us, hu, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
     DV_CUDA_OK(cudaMemcpyAsync(d_uc, hu + 2 * g->P, sizeof(AttnJobU) * 2 * P, cudaMemcpyHostToDevice, e->st));
     if (n_is) {
-      DV_CUDA_OK(cudaMemcpyAsync(d_is, hi_s, sizeof(int) * n_is, cudaMemcpyHostToDevice, e->st));
-      DV_CUDA_OK(cudaMemcpyAsync(d_ic, hi_c, sizeof(int) * n_ic, cudaMemcpyHostToDevice, e->st));
+      DV_CUDA_OK(cudaMemcpyAsync(d_is, hi_s, ib * n_is, cudaMemcpyHostToDevice, e->st));
+      DV_CUDA_OK(cudaMemcpyAsync(d_ic, hi_c, ib * n_ic, cudaMemcpyHostToDevice, e->st));
     }
     k_lg_load<<<dim3(8, 2 * P), 256, 0, e->st>>>(d_segs, g->Wr, g->x32, g->X2, g->cs, g->sn, g->rope16, g->kpts);
     DV_LAUNCHED(e, 1);
@@ -899,7 +901,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       DV_TRY(launch_gemm(L.p_qkv, T, e->st));
       if (!gemm_is_persistent())
         k_lg_rope<<<(unsigned)cdiv64((int64_t)T * 256, 256), 256, 0, e->st>>>(g->qkv, g->cs, g->sn, T);
-      if (n_is) DV_TRY(launch_lg_attn_persist(g->tm_qkv, d_us, d_is, n_is, octx, oldo, 0.125f, e->st));
+      if (n_is) DV_TRY(launch_lg_attn_persist(g->tm_qkv, d_is, n_is, octx, oldo, 0.125f, e->st));
       else if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_js, 0.125f));
       if (!g->fold_out) DV_TRY(launch_gemm(L.p_out, T, e->st));
@@ -909,7 +911,7 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       DV_TRY(launch_gemm(L.p_f3, T, e->st));
       // cross block
       DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
-      if (n_ic) DV_TRY(launch_lg_attn_persist(g->tm_qkv, d_uc, d_ic, n_ic, octx, oldo, 0.125f, e->st));
+      if (n_ic) DV_TRY(launch_lg_attn_persist(g->tm_qkv, d_ic, n_ic, octx, oldo, 0.125f, e->st));
       else if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_jc, 0.125f));
       if (!g->fold_out) DV_TRY(launch_gemm(L.pc_out, T, e->st));

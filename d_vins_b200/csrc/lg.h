@@ -39,8 +39,9 @@ int plan_lg_attn(CUtensorMap* tm, const __half* qkv, int T_cap);
 // ctx: output base, row stride ldo halves (256 = the ctx buffer; 512 = straight into the msg half of X2)
 int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int max_nq, __half* ctx, int ldo, float scale,
                    cudaStream_t st);
-// persistent variant: two resident CTAs per SM walk a cost-sorted list of (job << 8 | head << 4 | query tile) items
-int lg_attn_items(const AttnJobU* jobs, int n_jobs, int* items);     // host: builds the list, returns its length
-int launch_lg_attn_persist(const CUtensorMap& tm, const AttnJobU* jobs, const int* items, int n_items, __half* ctx, int ldo,
-                           float scale, cudaStream_t st);
+// persistent variant: two resident CTAs per SM walk a cost-sorted list of complete (job, head, query tile) descriptors
+int lg_attn_item_bytes();
+int lg_attn_items(const AttnJobU* jobs, int n_jobs, void* items_out);     // host: builds the list, returns its length
+int launch_lg_attn_persist(const CUtensorMap& tm, const void* items, int n_items, __half* ctx, int ldo, float scale,
+                           cudaStream_t st);
 }  // namespace dv

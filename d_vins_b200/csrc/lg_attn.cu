@@ -309,19 +309,46 @@ __global__ void __launch_bounds__(192, 2) lg_attn_umma_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Persistent variant (default, r02).  ncu of the kernel above at batch 32 (profiles/r02_attention_ncu.txt): MUFU pipe 30 %
-// busy, tensor pipe 19 %, 5.2 waves of 3072 CTAs of which a third exit at once - the steady-state chunk loop is fine, the
-// time goes into per-CTA set-up (barrier init, TMEM allocation, first Q/K/V round trip), the O read-out / store tail and
-// the wave quantisation of CTAs whose work differs 4 x (150- vs 662-token images).  Here TWO resident CTAs per SM walk a
-// host-built list of (job, head, query tile) items, most expensive first, in snake order over the CTAs (round r: CTA b
-// takes item r*G + b, odd rounds G-1-b), so barriers / TMEM are set up once, the TMA warp prefetches the next item's
-// Q/K/V under the current item's tail, and the softmax warps of the SM's two CTAs always have work for the MUFU pipe.
-// All barriers run on global counters (items n, chunks g) instead of per-CTA indices; q_empty releases the Q tile.
-template <bool LAZY>
-__global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,
-                                                                 const AttnJobU* __restrict__ jobs,
-                                                                 const int* __restrict__ items, int n_items,
-                                                                 __half* __restrict__ ctx, int ldo, float sl2) {
+// Persistent variant (default, r02).  ncu of the kernel above at batch 32 / 64 (profiles/README.md): MUFU pipe 30 % busy,
+// tensor pipe 19 %; a third of the 3072 CTAs exit at once, and the live ones spend their time in per-CTA set-up (barrier
+// init, TMEM allocation, first Q/K/V round trip), the O read-out tail, the wave quantisation of CTAs whose work differs
+// 4 x (150- vs 662-token images) and - in steady state - in the serial S -> softmax -> PV chain of a single row-owning
+// thread (stall samples: 25 % waiting for S, the exp2 sweep itself latency- not MUFU-bound at two softmax warps per SMSP).
+//  * TWO resident CTAs per SM walk a host-built list of (job, head, query tile) items, most expensive first, in snake
+//    order over the CTAs (round r: CTA b takes item r*G + b, odd rounds G-1-b): barriers / TMEM are set up once, the TMA
+//    warp prefetches the next item's Q/K/V under the current item's tail.  Barriers run on global counters (items n,
+//    chunks g); q_empty releases the Q tile.  Item descriptors are complete (no dependent job-table load) and fetched
+//    one item ahead.
+//  * EIGHT softmax warps: the two warps of a TMEM lane quarter share its 32 query rows, warp `half` owning the 32-key
+//    groups {2 half, 2 half + 1} of every 128-key chunk (its own P tile) and O columns [32 half, +32).  A row's running
+//    maximum / sum are combined through two spare TMEM columns (tcgen05.st -> named barrier -> tcgen05.ld): the chain
+//    per chunk halves and four softmax warps per SMSP keep the MUFU pipe fed.
+struct AttnItem { int q_row, rows, k_row, nk, q_col, k_col, v_col, o_col; };   // 32 bytes, see lg_attn_items()
+
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
+// value of the partner warp (same TMEM lanes, other column half) for this thread's row
+__device__ __forceinline__ float row_exchange(uint32_t col_own, uint32_t col_other, float v, int bar_id) {
+  tmem_st1(col_own, v);
+  tmem_st_wait();
+  tc_fence_before();
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  tc_fence_after();
+  const float o = tmem_ld1(col_other);
+  tmem_ld_wait();
+  return o;
+}
+
+__global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                 const AttnItem* __restrict__ items, int n_items,
+                                                                 __half* __restrict__ ctx, int ldo, float sl2,
+                                                                 long long* dbg) {
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -341,7 +368,7 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
     prefetch_tmap(&tmQKV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_full, 1); mbar_init(q_empty, 1);
+    mbar_init(s_full, 1); mbar_init(p_ready, 8); mbar_init(o_full, 1); mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 256);
@@ -349,32 +376,42 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();
-  // item of this CTA in round r (-1: none; then no later round has one either)
-  auto item_at = [&](int r) -> int {
+  // index of this CTA's item in round r (-1: none; then no later round has one either); descriptors are constants
+  // written by a host copy that precedes the whole LightGlue pass, so they may be read before the dependency wait
+  auto item_idx = [&](int r) -> int {
     const int idx = r * G + ((r & 1) ? G - 1 - bid : bid);
-    return idx < n_items ? __ldg(items + idx) : -1;
+    return idx < n_items ? idx : -1;
   };
+  auto load_item = [&](int idx, AttnItem& it) {
+    if (idx < 0) return;
+    const int4* p4 = reinterpret_cast<const int4*>(items + idx);
+    const int4 a = __ldg(p4), b = __ldg(p4 + 1);
+    it.q_row = a.x; it.rows = a.y; it.k_row = a.z; it.nk = a.w;
+    it.q_col = b.x; it.k_col = b.y; it.v_col = b.z; it.o_col = b.w;
+  };
+  int idx = item_idx(0);
+  AttnItem cur = {0, 0, 0, 0, 0, 0, 0, 0}, nxt = cur;
+  load_item(idx, cur);
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one_sync()) {
       int g = 0;
-      for (int n = 0;; ++n) {
-        const int it = item_at(n);
-        if (it < 0) break;
-        const AttnJobU jb = jobs[it >> 8];
-        const int head = (it >> 4) & 15, q0 = (it & 15) * 128;
-        const int n_chunks = (jb.nk + 127) >> 7;
+      for (int n = 0; idx >= 0; ++n) {
+        const int nidx = item_idx(n + 1);
+        load_item(nidx, nxt);
+        const int n_chunks = (cur.nk + 127) >> 7;
         if (n > 0) mbar_wait(q_empty, (n - 1) & 1);          // every S product of the previous item has read Q
         mbar_arrive_expect_tx(q_full, TILE_BYTES);
-        tma_load_2d(smem + OFF_Q, &tmQKV, q_full, jb.q_col + head * 64, jb.q_row + q0);
+        tma_load_2d(smem + OFF_Q, &tmQKV, q_full, cur.q_col, cur.q_row);
         for (int j = 0; j < n_chunks; ++j, ++g) {
           const int s = g & 1;
           mbar_wait(&kv_empty[s], ((g >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-          tma_load_2d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &kv_full[s], jb.k_col + head * 64, jb.k_row + j * 128);
-          tma_load_2d(smem + OFF_V + s * TILE_BYTES, &tmQKV, &kv_full[s], jb.v_col + head * 64, jb.k_row + j * 128);
+          tma_load_2d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &kv_full[s], cur.k_col, cur.k_row + j * 128);
+          tma_load_2d(smem + OFF_V + s * TILE_BYTES, &tmQKV, &kv_full[s], cur.v_col, cur.k_row + j * 128);
         }
+        cur = nxt; idx = nidx;
       }
     }
   } else if (warp == 1) {
@@ -384,11 +421,10 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
       const uint64_t dq = make_desc_sw128(smem_u32(smem + OFF_Q));
       const uint64_t dp = make_desc_sw128(smem_u32(smem + OFF_P));
       int g = 0;
-      for (int n = 0;; ++n) {
-        const int it = item_at(n);
-        if (it < 0) break;
-        const AttnJobU jb = jobs[it >> 8];
-        const int n_chunks = (jb.nk + 127) >> 7;
+      for (int n = 0; idx >= 0; ++n) {
+        const int nidx = item_idx(n + 1);
+        load_item(nidx, nxt);
+        const int n_chunks = (cur.nk + 127) >> 7;
         mbar_wait(q_full, n & 1);
         for (int j = 0; j < n_chunks; ++j, ++g) {
           const int s = g & 1;
@@ -403,55 +439,60 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
           if (j == n_chunks - 1) tc_commit(q_empty);
           mbar_wait(p_ready, g & 1);
           tc_fence_after();
-          const int pv_steps = min(8, (jb.nk - j * 128 + 15) >> 4);                // only the k-steps that hold valid keys
+          const int pv_steps = min(8, (cur.nk - j * 128 + 15) >> 4);               // only the k-steps that hold valid keys
           for (int k = 0; k < pv_steps; ++k)
+            // A: P tile (k >> 2), 32-byte step inside its 128-byte rows.  B: V rows [16k, 16k+16) = +2048 bytes.
             tc_mma_f16(tmem_base + 128, dp + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2),
-                       dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)(LAZY ? (j | k) != 0 : k != 0));
+                       dv + (uint64_t)(k * 128), idesc_pv, (uint32_t)((j | k) != 0));
           tc_commit(o_full);
           tc_commit(&kv_empty[s]);
         }
+        cur = nxt; idx = nidx;
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax / correction: thread == query row
-    const int q = warp & 3;
+    // ------------------------------------------------------------------ softmax: two threads (warps) per query row
+    const int q = warp & 3;                     // TMEM lane quarter
+    const int half = (warp - 2) >> 2;           // key groups {2 half, 2 half + 1} of a chunk; O columns [32 half, +32)
     const int row = q * 32 + lane;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint8_t* prow = smem + OFF_P + row * 128;
+    const uint32_t x_own = tl + 192 + half, x_oth = tl + 192 + (half ^ 1);     // exchange columns: row maximum
+    const uint32_t y_own = tl + 194 + half, y_oth = tl + 194 + (half ^ 1);     // ... row sum
+    const int bar_id = 1 + q;
+    uint8_t* ptile = smem + OFF_P + half * TILE_BYTES + row * 128;             // this warp's P tile row
+    const bool dbgt = dbg && bid == 3 && warp == 2 && lane == 0;               // DV_ATTN_DBG: cycle counters of one thread
+    long long d_s = 0, d_o = 0, d_sw = 0, d_x = 0, d_item = 0, d_ch = 0, d_end = 0;
     int g = 0;
-    for (int n = 0;; ++n) {
-      const int it = item_at(n);
-      if (it < 0) break;
-      const AttnJobU jb = jobs[it >> 8];
-      const int head = (it >> 4) & 15, q0 = (it & 15) * 128;
-      const int n_chunks = (jb.nk + 127) >> 7;
-      const bool warp_live = q0 + q * 32 < jb.nq;
-      float o[64];
-      if (!LAZY) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) o[i] = 0.f;
-      }
+    for (int n = 0; idx >= 0; ++n) {
+      const int nidx = item_idx(n + 1);
+      load_item(nidx, nxt);
+      const int n_chunks = (cur.nk + 127) >> 7;
+      const bool warp_live = q * 32 < cur.rows;
       float m_run = -INFINITY, l_run = 0.f;
+      if (dbgt) d_item += 1;
       for (int j = 0; j < n_chunks; ++j, ++g) {
+        const long long t0 = dbgt ? clock64() : 0;
         mbar_wait(s_full, g & 1);
         tc_fence_after();
+        if (dbgt) { d_s += clock64() - t0; d_ch += 1; }
         const int kbase = j * 128;
-        const int ngrp = min(4, (jb.nk - kbase + 31) >> 5);    // 32-key groups holding valid keys (PV reads no further)
-        if (!warp_live) {                                      // every row of this warp is >= nq: nothing to compute
+        const int ngrp = min(4, (cur.nk - kbase + 31) >> 5);   // 32-key groups holding valid keys (PV reads no further)
+        if (!warp_live) {                                      // every row of this lane quarter is padding
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cnt(p_ready);
-          if (!LAZY) mbar_wait(o_full, g & 1);
           continue;
         }
+        const int c0 = 2 * half, c1 = min(c0 + 2, ngrp);       // this warp's groups (none: chunk tail of <= 64 keys)
+        // P = exp2(s * sl2 - mb) of the own groups to shared memory (fp16, swizzled A operand), row sum, raw row maximum
         auto sweep = [&](float mb, float& sum, float& mx) {
 #pragma unroll 1
-          for (int c = 0; c < ngrp; ++c) {
+          for (int c = c0; c < c1; ++c) {
             uint32_t r[32];
             tmem_ld32(tl + c * 32, r);
             tmem_ld_wait();
             __align__(16) __half2 hv[16];
-            if (kbase + c * 32 + 32 <= jb.nk) {                 // full 32-key group (warp-uniform): no masking
+            if (kbase + c * 32 + 32 <= cur.nk) {                // full 32-key group (warp-uniform): no masking
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
@@ -466,40 +507,44 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
               for (int i = 0; i < 16; ++i) {
                 const int key = kbase + c * 32 + 2 * i;
                 const float s0 = __uint_as_float(r[2 * i]), s1 = __uint_as_float(r[2 * i + 1]);
-                if (key < jb.nk) mx = fmaxf(mx, s0);
-                if (key + 1 < jb.nk) mx = fmaxf(mx, s1);
-                const float p0 = key < jb.nk ? ex2_approx(fmaf(s0, sl2, -mb)) : 0.f;
-                const float p1 = key + 1 < jb.nk ? ex2_approx(fmaf(s1, sl2, -mb)) : 0.f;
+                if (key < cur.nk) mx = fmaxf(mx, s0);
+                if (key + 1 < cur.nk) mx = fmaxf(mx, s1);
+                const float p0 = key < cur.nk ? ex2_approx(fmaf(s0, sl2, -mb)) : 0.f;
+                const float p1 = key + 1 < cur.nk ? ex2_approx(fmaf(s1, sl2, -mb)) : 0.f;
                 hv[i] = __floats2half2_rn(p0, p1);
                 sum += p0 + p1;
               }
             }
-            uint8_t* tile = prow + (c >> 1) * TILE_BYTES;
             const int ch0 = (c & 1) * 4;
 #pragma unroll
             for (int gg = 0; gg < 4; ++gg)
-              *reinterpret_cast<uint4*>(tile + (((ch0 + gg) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[gg];
+              *reinterpret_cast<uint4*>(ptile + (((ch0 + gg) ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[gg];
           }
         };
-        float corr = 1.f, sum = 0.f;
-        if (LAZY && j > 0) {
+        float sum = 0.f;
+        if (j > 0) {
           // PV(j-1) has retired (it precedes S(j) on the tensor pipe): the P tiles may be overwritten, O is stable.
+          // SINGLE sweep with the current scaling reference m_run; only if some row's maximum outgrew it by 2^8 (rare
+          // after the first chunk) is O rescaled in TMEM and the sweep repeated with the new reference.
+          const long long t1 = dbgt ? clock64() : 0;
           mbar_wait(o_full, (g - 1) & 1);
           tc_fence_after();
+          const long long t2 = dbgt ? clock64() : 0;
           float mx = -INFINITY;
           sweep(m_run * sl2, sum, mx);
-          const bool grow = (mx - m_run) * sl2 > 8.f;
+          const long long t3 = dbgt ? clock64() : 0;
+          mx = fmaxf(mx, row_exchange(x_own, x_oth, mx, bar_id));
+          if (dbgt) { const long long t4 = clock64(); d_o += t2 - t1; d_sw += t3 - t2; d_x += t4 - t3; }
+          const bool grow = (mx - m_run) * sl2 > 8.f;          // identical in both warps of the row
           if (__any_sync(0xffffffffu, grow)) {
+            float corr = 1.f;
             if (grow) { corr = ex2_approx((m_run - mx) * sl2); m_run = mx; l_run *= corr; }
+            uint32_t r[32];
+            tmem_ld32(tl + 128 + half * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t r[32];
-              tmem_ld32(tl + 128 + c * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
-              tmem_st32(tl + 128 + c * 32, r);
-            }
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+            tmem_st32(tl + 128 + half * 32, r);
             tmem_st_wait();
             sum = 0.f;
             float unused = -INFINITY;
@@ -508,27 +553,20 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
         } else {
           float mx = -INFINITY;
 #pragma unroll 1
-          for (int c = 0; c < ngrp; ++c) {
+          for (int c = c0; c < c1; ++c) {
             uint32_t r[32];
             tmem_ld32(tl + c * 32, r);
             tmem_ld_wait();
-            if (kbase + c * 32 + 32 <= jb.nk) {
+            if (kbase + c * 32 + 32 <= cur.nk) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (kbase + c * 32 + i < jb.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+                if (kbase + c * 32 + i < cur.nk) mx = fmaxf(mx, __uint_as_float(r[i]));
             }
           }
-          if (LAZY) {
-            m_run = mx;                                         // first chunk: the reference is its own maximum
-          } else {
-            const float m_new = fmaxf(m_run, mx);               // finite: every chunk holds >= 1 valid key
-            corr = ex2_approx((m_run - m_new) * sl2);
-            m_run = m_new;
-            l_run *= corr;
-          }
+          m_run = fmaxf(mx, row_exchange(x_own, x_oth, mx, bar_id));   // first chunk: the reference is its own maximum
           float unused = -INFINITY;
           sweep(m_run * sl2, sum, unused);
         }
@@ -537,52 +575,38 @@ __global__ void __launch_bounds__(192, 2) lg_attn_persist_kernel(const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cnt(p_ready);
-        if (!LAZY) {
-          if (__any_sync(0xffffffffu, corr != 1.f)) {          // the running maxima settle after the first chunks
-#pragma unroll
-            for (int i = 0; i < 64; ++i) o[i] *= corr;
-          }
-          mbar_wait(o_full, g & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tl + 128 + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(r[i]);
-          }
-          tc_fence_before();     // order these TMEM reads before the next chunk's MMAs (released through p_ready / s_full)
-        }
       }
-      if (LAZY) {
-        // PV of the item's last chunk has retired: O is complete, and the P tiles / the O columns may be rewritten by the
-        // next item.  EVERY warp waits (a warp that idled through this item may be live in the next one).
-        mbar_wait(o_full, (g - 1) & 1);
-        tc_fence_after();
-        if (warp_live) {
+      // PV of the item's last chunk has retired: O is complete, and the P tiles / the O columns may be rewritten by the
+      // next item.  EVERY warp waits (a warp that idled through this item may be live in the next one).
+      const long long te = dbgt ? clock64() : 0;
+      mbar_wait(o_full, (g - 1) & 1);
+      tc_fence_after();
+      if (dbgt) d_end += clock64() - te;
+      if (warp_live) {
+        const float l_tot = l_run + row_exchange(y_own, y_oth, l_run, bar_id);
+        uint32_t r[32];
+        tmem_ld32(tl + 128 + half * 32, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        if (row < cur.rows) {
+          const float inv = 1.f / l_tot;
+          __half* op = ctx + (int64_t)(cur.q_row + row) * ldo + cur.o_col + half * 32;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tl + 128 + c * 32, r);
-            tmem_ld_wait();
+          for (int gg = 0; gg < 4; ++gg) {
+            __align__(16) __half2 hv[4];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[c * 32 + i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 4; ++i)
+              hv[i] = __floats2half2_rn(__uint_as_float(r[gg * 8 + 2 * i]) * inv, __uint_as_float(r[gg * 8 + 2 * i + 1]) * inv);
+            reinterpret_cast<uint4*>(op)[gg] = *reinterpret_cast<const uint4*>(hv);
           }
         }
+      } else {
         tc_fence_before();
       }
-      if (q0 + row < jb.nq) {
-        const float inv = 1.f / l_run;
-        __half* op = ctx + (int64_t)(jb.q_row + q0 + row) * ldo + head * 64;
-#pragma unroll
-        for (int gg = 0; gg < 8; ++gg) {
-          __align__(16) __half2 hv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) hv[i] = __floats2half2_rn(o[gg * 8 + 2 * i] * inv, o[gg * 8 + 2 * i + 1] * inv);
-          reinterpret_cast<uint4*>(op)[gg] = *reinterpret_cast<const uint4*>(hv);
-        }
-      }
+      cur = nxt; idx = nidx;
+    }
+    if (dbgt) {
+      dbg[0] += d_s; dbg[1] += d_o; dbg[2] += d_sw; dbg[3] += d_x; dbg[4] += d_ch; dbg[5] += d_item; dbg[6] += d_end;
     }
   }
   tc_fence_before();
@@ -598,8 +622,7 @@ static int g_attn_sms = 148;
 int lg_attn_init() {
   DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DV_CUDA_OK(cudaFuncSetAttribute(lg_attn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   int dev = 0;
   DV_CUDA_OK(cudaGetDevice(&dev));
   DV_CUDA_OK(cudaDeviceGetAttribute(&g_attn_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -636,39 +659,53 @@ int launch_lg_attn(const CUtensorMap& tm, const AttnJobU* jobs, int n_jobs, int 
   return DV_OK;
 }
 
-// Persistent launch: `items` = device list of (job << 8 | head << 4 | query tile), most expensive first (lg_attn_items).
-int launch_lg_attn_persist(const CUtensorMap& tm, const AttnJobU* jobs, const int* items, int n_items, __half* ctx, int ldo,
-                           float scale, cudaStream_t st) {
+// Persistent launch: `items` = device list built by lg_attn_items(), most expensive first.
+int launch_lg_attn_persist(const CUtensorMap& tm, const void* items, int n_items, __half* ctx, int ldo, float scale,
+                           cudaStream_t st) {
   if (n_items <= 0) return DV_OK;
-  static const bool lazy = [] { const char* e = getenv("DV_ATTN_LAZY"); return !(e && e[0] == '0'); }();   // A/B switch
   const int grid = n_items < 2 * g_attn_sms ? n_items : 2 * g_attn_sms;
-  if (lazy)
-    DV_CUDA_OK(launch_pdl(lg_attn_persist_kernel<true>, dim3(grid), dim3(192), (size_t)SMEM_BYTES, st, tm, jobs, items, n_items,
-                          ctx, ldo, scale * 1.4426950408889634f));
-  else
-    DV_CUDA_OK(launch_pdl(lg_attn_persist_kernel<false>, dim3(grid), dim3(192), (size_t)SMEM_BYTES, st, tm, jobs, items, n_items,
-                          ctx, ldo, scale * 1.4426950408889634f));
+  static long long* d_dbg = nullptr;
+  static const bool want = getenv("DV_ATTN_DBG") != nullptr;       // diagnostics: cycle counters of one softmax thread
+  static int calls = 0;
+  if (want && !d_dbg) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+  DV_CUDA_OK(launch_pdl(lg_attn_persist_kernel, dim3(grid), dim3(320), (size_t)SMEM_BYTES, st, tm,
+                        reinterpret_cast<const AttnItem*>(items), n_items, ctx, ldo, scale * 1.4426950408889634f,
+                        want ? d_dbg : (long long*)nullptr));
   DV_CUDA_OK(cudaGetLastError());
+  if (want && ++calls % 18 == 0) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    cudaMemset(d_dbg, 0, 64);
+    fprintf(stderr, "[attn dbg] CTA 3 warp 2 over 18 launches: chunks %lld items %lld | cycles/chunk: wait S %lld, wait O %lld, sweep %lld, "
+            "exchange %lld | item-end O wait %lld per item\n", h[4], h[5], h[0] / (h[4] ? h[4] : 1), h[1] / (h[4] ? h[4] : 1),
+            h[2] / (h[4] ? h[4] : 1), h[3] / (h[4] ? h[4] : 1), h[6] / (h[5] ? h[5] : 1));
+  }
   return DV_OK;
 }
 
-// Host side of the item list: every (job, head, 128-query tile) of `jobs`, sorted by decreasing cost.  A tile occupies its
-// CTA for (32-key groups of the key side) sweeps whatever its number of live rows, so the key count ranks first and the
-// live 32-row warps (MUFU work) break ties.  Returns the number of items written (<= n_jobs * 4 * 8).
-int lg_attn_items(const AttnJobU* jobs, int n_jobs, int* items) {
-  struct It { int cost, code; };
+// Host side of the item list: every (job, head, 128-query tile) of `jobs` as a complete 32-byte descriptor, sorted by
+// decreasing cost.  A tile occupies its CTA for (32-key groups of the key side) sweeps whatever its number of live rows,
+// so the key count ranks first and the live 32-row quarters (MUFU work) break ties.  Returns the number of items.
+int lg_attn_item_bytes() { return (int)sizeof(AttnItem); }
+int lg_attn_items(const AttnJobU* jobs, int n_jobs, void* items_out) {
+  struct It { int cost; AttnItem it; };
   static thread_local std::vector<It> tmp;
   tmp.clear();
   for (int jn = 0; jn < n_jobs; ++jn) {
-    const int groups = (jobs[jn].nk + 31) >> 5;
-    for (int qt = 0; qt * 128 < jobs[jn].nq; ++qt) {
-      const int rows = jobs[jn].nq - qt * 128 < 128 ? jobs[jn].nq - qt * 128 : 128;
+    const AttnJobU& jb = jobs[jn];
+    const int groups = (jb.nk + 31) >> 5;
+    for (int qt = 0; qt * 128 < jb.nq; ++qt) {
+      const int rows = jb.nq - qt * 128 < 128 ? jb.nq - qt * 128 : 128;
       const int cost = groups * 8 + ((rows + 31) >> 5);
-      for (int h = 0; h < 4; ++h) tmp.push_back({cost, (jn << 8) | (h << 4) | qt});
+      for (int h = 0; h < 4; ++h)
+        tmp.push_back({cost, {jb.q_row + qt * 128, rows, jb.k_row, jb.nk, jb.q_col + h * 64, jb.k_col + h * 64,
+                              jb.v_col + h * 64, h * 64}});
     }
   }
-  std::stable_sort(tmp.begin(), tmp.end(), [](const It& a, const It& b) { return a.cost > b.cost; });
-  for (size_t i = 0; i < tmp.size(); ++i) items[i] = tmp[i].code;
+  std::stable_sort(tmp.begin(), tmp.end(), [](const It& x, const It& y) { return x.cost > y.cost; });
+  AttnItem* out = reinterpret_cast<AttnItem*>(items_out);
+  for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i].it;
   return (int)tmp.size();
 }
 
