@@ -115,7 +115,7 @@ int conv_halo_init();
 // ---- halo-tile 3x3 convolution for 64/128 -> 128k channels (conv_halo128.cu): 32x8-pixel tiles (two M=128 row blocks),
 // activations fetched once per tile, weights streamed through a ring of [128 x 64] blocks.  Input channel-blocked.
 struct Halo128Plan {
-  CUtensorMap tmX, tmW;
+  CUtensorMap tmX, tmW, tmWh;     // tmWh: [64 x 64] half-blocks for the CTA-pair kernel
   int H = 0, W = 0, n_cap = 0, tiles_w = 0, tiles_h = 0, cin = 0, cout = 0;
   const float* bias = nullptr;
   __half* out = nullptr;

@@ -75,7 +75,9 @@ def test_conv3x3_halo64(eng, n, h, w, pool, blocked):
 @pytest.mark.parametrize("n,h,w,cin,cout,pool,blocked", [
     (1, 32, 8, 128, 128, False, True), (1, 32, 8, 64, 128, False, False), (2, 40, 24, 128, 128, True, True),
     (1, 37, 29, 128, 128, True, False), (1, 37, 29, 64, 128, False, True), (2, 60, 94, 128, 512, False, False),
-    (3, 120, 188, 128, 128, True, True), (2, 47, 155, 128, 256, False, True)])
+    (3, 120, 188, 128, 128, True, True), (2, 47, 155, 128, 256, False, True),
+    # CTA-pair kernel with an ODD tile count (the odd CTA of the last pair has no tile), one / three images
+    (1, 16, 40, 128, 128, False, False), (3, 32, 24, 64, 128, True, True), (3, 32, 24, 128, 256, False, False)])
 def test_conv3x3_halo128(eng, n, h, w, cin, cout, pool, blocked):
     """256-pixel halo-tile kernel (conv_halo128.cu): halo fetched once per 32x8 tile, weights streamed, two M=128 row
     blocks per weight block; ragged tiles, odd sizes (pool floors), several 128-column output chunks."""

@@ -8,5 +8,5 @@ try:
 except Exception as ex: print("$name FAILED", ex)
 PY
 }
-run persist0 DV_ATTN_PERSIST=0
-run persist1 DV_ATTN_PERSIST=1
+run h128pair0 DV_SP_HALO128_PAIR=0
+run h128pair1 DV_SP_HALO128_PAIR=1

@@ -1,2 +1,3 @@
 cd $GRAFT_REPO_ROOT
-DV_ATTN_DBG=1 timeout 300 python bench.py --steps 2 --warmup 3 --no-latency --no-cpu-baseline 2>&1 >/dev/null | grep "attn dbg" | tail -4
+echo "--- plain 300 400"; timeout 120 python tools/attn_probe.py 300 400 2>&1 | tail -n 3
+echo "--- plain 150 662"; timeout 120 python tools/attn_probe.py 150 662 2>&1 | tail -n 3
