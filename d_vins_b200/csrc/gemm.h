@@ -89,6 +89,20 @@ bool gemm_pair_eligible(const GemmPlan& pl, long m_tiles);
 int gemm_pair_init();
 int launch_gemm_pair(const GemmPlan& pl, const GemmParams& p, long m_tiles, cudaStream_t st);
 
+// ---- LightGlue FFN first half in one kernel (lg_ffn0.cu): GELU(LayerNorm512(W0 . [x | ctx] + b0)), clusters of four CTAs
+struct Ffn0Plan {
+  CUtensorMap tmA, tmB;
+  mutable CUtensorMap tmO16;
+  mutable int out_rows = -1;
+  const float *bias = nullptr, *gamma = nullptr, *beta = nullptr;
+  __half* out = nullptr;
+  int ldo = 0, rows_cap = 0;
+};
+int lg_ffn0_init();
+int plan_lg_ffn0(Ffn0Plan* pl, const __half* A, int lda, int T_cap, const __half* W, const float* bias, const float* gamma,
+                 const float* beta, __half* out, int ldo);
+int launch_lg_ffn0(const Ffn0Plan& pl, int rows, cudaStream_t st);
+
 // ---- weights-stationary halo-tile 3x3 convolution, 64 -> 64 channels (conv_halo.cu) -------------------------------
 // Activations in the channel-blocked layout [N][C/8][H][W][8] ("NC/8HWC8"): one TMA box per 16x8-pixel output tile
 // brings the 18x10 halo ONCE; the nine tap operands are views of it (no-swizzle UMMA descriptors with shifted start

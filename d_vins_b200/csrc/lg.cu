@@ -34,6 +34,7 @@ struct LgLayer {
   float *bqkv, *bout, *bf0, *bf3, *bcqkv, *bcout, *bcf0, *bcf3;
   float *ln_g, *ln_b, *cln_g, *cln_b;
   GemmPlan p_qkv, p_out, p_f0, p_f3, pc_qkv, pc_out, pc_f0, pc_f3;
+  Ffn0Plan pf_f0, pfc_f0;              // fused ffn.0 + LayerNorm + GELU (lg_ffn0.cu)
 };
 
 struct LgNet {
@@ -44,6 +45,8 @@ struct LgNet {
   // two linear maps with nothing in between compose offline (like folding BatchNorm into a convolution), so the
   // attention writes its context straight into the second half of X2 and one GEMM launch per block disappears.
   bool fold_out = true;
+  bool fuse_ffn0 = true;               // DV_LG_FUSE_FFN0=0: GEMM + k_lg_ln_gelu as two kernels (A/B); =2: fused at any size
+  bool fuse_ffn0_always = false;
   float* Wr = nullptr;                 // [32,2]
   LgLayer L[LG_LAYERS];
   __half* wfinal = nullptr; float* bfinal = nullptr;   // pre-scaled by 256^-1/4
@@ -647,6 +650,8 @@ int lg_init(Engine* e) {
   g->segcap = (e->cfg.lg_max_kpts + 127) & ~127;
   g->Tcap = g->P * 2 * g->segcap;
   { const char* env = getenv("DV_LG_FOLD_OUT"); g->fold_out = !(env && env[0] == '0'); }
+  { const char* env = getenv("DV_LG_FUSE_FFN0"); g->fuse_ffn0 = !(env && env[0] == '0'); g->fuse_ffn0_always = env && env[0] == '2'; }
+  DV_TRY(lg_ffn0_init());
   DV_CUDA_OK(cudaFuncSetAttribute(k_lg_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   const int T = g->Tcap, P = g->P, SC = g->segcap;
   {
@@ -768,11 +773,13 @@ int lg_init(Engine* e) {
       DV_TRY(plan_gemm(&L.p_qkv, g->X2, 512, T, L.wqkv, 256, 768, 256, ep)); }
     DV_TRY(plan_gemm(&L.p_out, g->ctx, 256, T, L.wout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bout)));
     DV_TRY(plan_gemm(&L.p_f0, g->X2, 512, T, L.wf0, 512, 512, 512, ep16(g->ffh, 512, L.bf0)));
+    DV_TRY(plan_lg_ffn0(&L.pf_f0, g->X2, 512, T, L.wf0, L.bf0, L.ln_g, L.ln_b, g->ffg, 512));
     { EpiParams ep; ep.out32 = g->x32; ep.ld32 = 256; ep.res32 = g->x32; ep.ldr32 = 256; ep.out16 = g->X2; ep.ld16 = 512; ep.bias = L.bf3;
       DV_TRY(plan_gemm(&L.p_f3, g->ffg, 512, T, L.wf3, 512, 256, 512, ep)); }
     DV_TRY(plan_gemm(&L.pc_qkv, g->X2, 512, T, L.cqkv, 256, 512, 256, ep16(g->qkv, 768, L.bcqkv)));
     DV_TRY(plan_gemm(&L.pc_out, g->ctx, 256, T, L.cout, 256, 256, 256, ep16(g->X2 + 256, 512, L.bcout)));
     DV_TRY(plan_gemm(&L.pc_f0, g->X2, 512, T, L.cf0, 512, 512, 512, ep16(g->ffh, 512, L.bcf0)));
+    DV_TRY(plan_lg_ffn0(&L.pfc_f0, g->X2, 512, T, L.cf0, L.bcf0, L.cln_g, L.cln_b, g->ffg, 512));
     { EpiParams ep; ep.out32 = g->x32; ep.ld32 = 256; ep.res32 = g->x32; ep.ldr32 = 256; ep.out16 = g->X2; ep.ld16 = 512; ep.bias = L.bcf3;
       DV_TRY(plan_gemm(&L.pc_f3, g->ffg, 512, T, L.cf3, 512, 256, 512, ep)); }
   }
@@ -895,6 +902,9 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
     DV_LAUNCHED(e, 1);
     if (after_load && *after_load) DV_TRY((*after_load)());
     const dim3 agrid(cdiv(max_n_any, ATT_QT), LG_HEADS, 2 * P);
+    // the four-CTA-cluster kernel pays off once every cluster has a few row tiles; a single pair (the B = 1 latency path,
+    // ~830 tokens) is 3 % faster with the two small kernels
+    const bool fused0 = g->fuse_ffn0 && (T >= 2048 || g->fuse_ffn0_always);
     for (int i = 0; i < LG_LAYERS; ++i) {
       LgLayer& L = g->L[i];
       // self block
@@ -905,9 +915,13 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       else if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_us, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_js, 0.125f));
       if (!g->fold_out) DV_TRY(launch_gemm(L.p_out, T, e->st));
-      DV_TRY(launch_gemm(L.p_f0, T, e->st));
-      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
-                            (const float*)L.ln_b, g->ffg, (int64_t)T));
+      if (fused0) {
+        DV_TRY(launch_lg_ffn0(L.pf_f0, T, e->st));
+      } else {
+        DV_TRY(launch_gemm(L.p_f0, T, e->st));
+        DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.ln_g,
+                              (const float*)L.ln_b, g->ffg, (int64_t)T));
+      }
       DV_TRY(launch_gemm(L.p_f3, T, e->st));
       // cross block
       DV_TRY(launch_gemm(L.pc_qkv, T, e->st));
@@ -915,11 +929,15 @@ int lg_run(Engine* e, int P, const LgSeg* segs_in, const std::function<int()>* a
       else if (g->attn_umma) DV_TRY(launch_lg_attn(g->tm_qkv, d_uc, 2 * P, max_n_any, octx, oldo, 0.125f, e->st));
       else DV_CUDA_OK(launch_pdl(k_lg_attention, agrid, dim3(ATT_WARPS * 32), ATT_SMEM, e->st, (const AttnJob*)d_jc, 0.125f));
       if (!g->fold_out) DV_TRY(launch_gemm(L.pc_out, T, e->st));
-      DV_TRY(launch_gemm(L.pc_f0, T, e->st));
-      DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
-                            (const float*)L.cln_b, g->ffg, (int64_t)T));
+      if (fused0) {
+        DV_TRY(launch_lg_ffn0(L.pfc_f0, T, e->st));
+      } else {
+        DV_TRY(launch_gemm(L.pc_f0, T, e->st));
+        DV_CUDA_OK(launch_pdl(k_lg_ln_gelu, dim3(g->ln_grid), dim3(256), 0, e->st, (const __half*)g->ffh, (const float*)L.cln_g,
+                              (const float*)L.cln_b, g->ffg, (int64_t)T));
+      }
       DV_TRY(launch_gemm(L.pc_f3, T, e->st));
-      DV_LAUNCHED(e, g->fold_out ? 10 : 12);
+      DV_LAUNCHED(e, (g->fold_out ? 10 : 12) - (fused0 ? 2 : 0));
     }
     DV_CUDA_OK(cudaGetLastError());
     DV_TRY(launch_gemm(g->p_final, T, e->st));

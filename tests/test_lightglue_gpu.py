@@ -99,3 +99,41 @@ def test_lightglue_rejects_small_inputs(eng):
     z = np.zeros((5, 2), np.float32); d = np.zeros((5, 256), np.float32)
     with pytest.raises(capi.DvError):
         eng.lg_match(z, z, d, d, 480, 752, 480, 752)
+
+
+def test_fused_ffn0_matches_two_kernel_path():
+    """lg_ffn0.cu (ffn.0 + LayerNorm + GELU in one four-CTA-cluster kernel, row statistics exchanged through
+    distributed shared memory) against the GEMM + k_lg_ln_gelu pair on the same pair: identical match pairs, scores
+    within the float tolerance (the fused kernel sums the LayerNorm statistics in a different order)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.getcwd())
+import bench
+from d_vins_b200 import capi
+e = capi.Engine(height=480, width=752, weights_path=bench.make_weights())
+rng = np.random.default_rng(5)
+N, M = 662, 150
+d1 = rng.standard_normal((N, 256)).astype(np.float32); d1 /= np.linalg.norm(d1, axis=1, keepdims=True)
+perm = rng.permutation(N)[:M]
+d0 = d1[perm] + 0.03 * rng.standard_normal((M, 256)).astype(np.float32); d0 /= np.linalg.norm(d0, axis=1, keepdims=True)
+k1 = np.stack([rng.uniform(8, 744, N), rng.uniform(8, 472, N)], 1).astype(np.float32)
+k0 = k1[perm] + rng.normal(0, 1, (M, 2)).astype(np.float32)
+m, s = e.lg_match(k0, k1, d0, d1, 480, 752, 480, 752)
+print(json.dumps({"m": m.tolist(), "s": s.tolist()}))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("0", "2"):
+        env = dict(os.environ, DV_LG_FUSE_FFN0=mode)
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        import json
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert len(a["m"]) >= 20
+    assert a["m"] == b["m"]
+    assert np.abs(np.log(np.array(a["s"])) - np.log(np.array(b["s"]))).max() < 0.05
