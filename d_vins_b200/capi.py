@@ -58,6 +58,29 @@ _lib = load_library()
 _lib.dv_last_error.restype = C.c_char_p
 _lib.dv_version.restype = C.c_char_p
 _lib.dv_config_default.restype = None
+LOG_SINK = C.CFUNCTYPE(None, C.c_int32, C.c_char_p, C.c_void_p)
+_lib.dv_log_set_level.restype = None
+_lib.dv_log_set_level.argtypes = [C.c_int32]
+_lib.dv_log_get_level.restype = C.c_int32
+_lib.dv_log_set_sink.restype = None
+_lib.dv_log_set_sink.argtypes = [LOG_SINK, C.c_void_p]
+_sink_keepalive = [None]
+
+
+def log_set_level(level: int) -> None:
+    """0 off, 1 error, 2 warning (default), 3 info, 4 debug (ilogger.hpp:24-29 levels, minus FATAL's abort)."""
+    _lib.dv_log_set_level(int(level))
+
+
+def log_set_sink(fn) -> None:
+    """fn(level, message) receives every log line instead of stderr; None restores stderr."""
+    if fn is None:
+        _lib.dv_log_set_sink(C.cast(None, LOG_SINK), None)
+        _sink_keepalive[0] = None
+        return
+    cb = LOG_SINK(lambda lvl, msg, user: fn(int(lvl), (msg or b"").decode(errors="replace")))
+    _sink_keepalive[0] = cb
+    _lib.dv_log_set_sink(cb, None)
 
 
 def _ptr(a, ctype):

@@ -118,6 +118,7 @@ dv_status dv_comm_init(dv_engine* h, const void* id128) {
   memcpy(&id, id128, 128);
   ncclResult_t r = g_api->CommInitRank(&e->comm->comm, e->cfg.world_size, id, e->cfg.rank);
   if (r != ncclSuccess) { comm_free(e); return (dv_status)nccl_fail("ncclCommInitRank", r); }
+  log_msg(3, "NCCL communicator up: rank %d of %d; exchanging CUDA-IPC handles of the feature stores", e->cfg.rank, e->cfg.world_size);
   return (dv_status)store_exchange_peers(e);     // CUDA-IPC views of every rank's feature store (one-sided P2P pulls)
 }
 

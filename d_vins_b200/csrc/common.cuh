@@ -11,6 +11,9 @@ namespace dv {
 // Sticky error text of the calling thread's last failure (surfaced through dv_last_error()).
 void set_error(const std::string& msg);
 const char* get_error();
+// levelled logger behind dv_log_set_level / dv_log_set_sink (1 error .. 4 debug); printf-style
+void log_msg(int level, const char* fmt, ...);
+bool log_enabled(int level);
 
 #define DV_CUDA_OK(expr)                                                                     \
   do {                                                                                       \

@@ -1,5 +1,10 @@
 // C-ABI implementation: engine lifetime, per-keyframe and batched entry points, measurement hooks.
 // The heavy lifting lives in sp.cu / mix.cu / lg.cu / knn.cu / gemm_umma.cu.
+#include <stdarg.h>
+
+#include <atomic>
+#include <mutex>
+
 #include "engine.h"
 
 #include <math.h>
@@ -12,7 +17,24 @@
 namespace dv {
 
 static thread_local std::string g_err;
-void set_error(const std::string& msg) { g_err = msg; }
+static std::atomic<int> g_log_level{[] { const char* e = getenv("DV_LOG"); return e ? atoi(e) : 2; }()};
+static std::mutex g_log_mu;
+static dv_log_sink g_log_sink = nullptr;
+static void* g_log_user = nullptr;
+bool log_enabled(int level) { return level <= g_log_level.load(std::memory_order_relaxed); }
+void log_msg(int level, const char* fmt, ...) {
+  if (!log_enabled(level)) return;
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  std::lock_guard<std::mutex> lk(g_log_mu);
+  if (g_log_sink) { g_log_sink(level, buf, g_log_user); return; }
+  static const char* names[5] = {"", "error", "warn", "info", "debug"};
+  fprintf(stderr, "[dvins %s] %s\n", names[level < 1 ? 1 : (level > 4 ? 4 : level)], buf);
+}
+void set_error(const std::string& msg) { g_err = msg; log_msg(1, "%s", msg.c_str()); }
 const char* get_error() { return g_err.c_str(); }
 
 // Device scratch of the dv_dbg_* entry points: released on every return path (DV_CUDA_OK returns early on failure).
@@ -67,6 +89,13 @@ void dv_config_default(dv_config* c) {
 }
 
 const char* dv_last_error(void) { return dv::get_error(); }
+void dv_log_set_level(int32_t level) { dv::g_log_level.store(level < 0 ? 0 : (level > 4 ? 4 : level)); }
+int32_t dv_log_get_level(void) { return dv::g_log_level.load(); }
+void dv_log_set_sink(dv_log_sink sink, void* user) {
+  std::lock_guard<std::mutex> lk(dv::g_log_mu);
+  dv::g_log_sink = sink;
+  dv::g_log_user = user;
+}
 const char* dv_version(void) { return "d_vins_b200 0.1 (sm_100a)"; }
 
 dv_status dv_create(const dv_config* cfg, dv_engine** out) {
@@ -135,6 +164,14 @@ dv_status dv_create(const dv_config* cfg, dv_engine** out) {
   if ((rc = store_init(e))) return fail(rc);
   if (cudaStreamSynchronize(e->st) != cudaSuccess) { set_error("engine init: device error"); return fail(DV_ERR_CUDA); }
   e->weights.clear();   // host copies no longer needed
+  {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    log_msg(3, "engine created: %dx%d, max_batch %d, max_kpts %d, max_vio %d, bank %lld rows, store %d keyframes, rank %d/%d, "
+            "weights %s, device memory in use %.1f GB of %.1f GB", e->H, e->W, e->B, e->cfg.max_kpts, e->cfg.max_vio,
+         (long long)e->cfg.bank_capacity, e->cfg.store_capacity, e->cfg.rank, e->cfg.world_size,
+         e->cfg.weights_path ? e->cfg.weights_path : "(none: stage-level entry points only)", (tot - fr) / 1e9, tot / 1e9);
+  }
   *out = reinterpret_cast<dv_engine*>(e);
   return DV_OK;
 }

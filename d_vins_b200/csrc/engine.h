@@ -175,8 +175,10 @@ int run_graphed(Engine* e, GraphCache& gc, F&& enqueue) {
       cudaGetLastError();
       gc.exec = nullptr;
       gc.failed = true;
+      log_msg(2, "CUDA graph instantiation failed (%s): this launch sequence stays eager", cudaGetErrorString(ci));
       return enqueue();
     }
+    log_msg(4, "captured a CUDA graph of %lld kernel launches", (long long)gc.launches);
   }
   e->launches += gc.launches;
   DV_CUDA_OK(cudaGraphLaunch(gc.exec, e->st));

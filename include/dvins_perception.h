@@ -67,6 +67,15 @@ void dv_config_default(dv_config* cfg);
 const char* dv_last_error(void);
 const char* dv_version(void);
 
+/* Levelled logger (replaces iLogger, tensorrt_tools/ilogger.hpp:24-29 / ilogger.cpp:385-440: printf-style INFO* macros with
+ * an optional file sink).  Levels: 0 off, 1 error, 2 warning, 3 info, 4 debug; default 2, or the DV_LOG environment
+ * variable at load time.  Every failure reported through dv_last_error() is also logged at level 1.  Messages go to
+ * stderr unless a sink is installed; the sink is called on the thread that logs. */
+typedef void (*dv_log_sink)(int32_t level, const char* message, void* user);
+void dv_log_set_level(int32_t level);
+int32_t dv_log_get_level(void);
+void dv_log_set_sink(dv_log_sink sink, void* user);
+
 /* Factories single_init / creat_mix / creat_estimator (deep_net.cpp:1184-1203, :1445) load four TensorRT engines
  * at static-init time and return unchecked null pointers on failure; here: one explicit, checked call. */
 dv_status dv_create(const dv_config* cfg, dv_engine** out);

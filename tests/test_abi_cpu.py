@@ -51,6 +51,28 @@ def test_bad_config_rejected_before_touching_cuda():
     assert b"size mismatch" in capi._lib.dv_last_error()
 
 
+def test_logger_levels_and_sink():
+    """Levelled logger (ilogger.hpp:24-29): failures are logged at level 1 through the installed sink; level 0
+    silences them."""
+    from d_vins_b200 import capi
+    seen = []
+    capi.log_set_sink(lambda lvl, msg: seen.append((lvl, msg)))
+    try:
+        capi.log_set_level(2)
+        cfg = capi.default_config()
+        cfg.struct_size = 4
+        h = ctypes.c_void_p()
+        assert capi._lib.dv_create(ctypes.byref(cfg), ctypes.byref(h)) == 1
+        assert seen and seen[-1][0] == 1 and "size mismatch" in seen[-1][1]
+        n = len(seen)
+        capi.log_set_level(0)
+        assert capi._lib.dv_create(ctypes.byref(cfg), ctypes.byref(h)) == 1
+        assert len(seen) == n and capi._lib.dv_log_get_level() == 0
+    finally:
+        capi.log_set_level(2)
+        capi.log_set_sink(None)
+
+
 def test_product_never_imports_oracle():
     """The product package must not import, call or link anything under oracle/."""
     pkg = os.path.join(ROOT, "d_vins_b200")
