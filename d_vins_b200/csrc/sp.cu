@@ -29,6 +29,7 @@ struct SpNet {
   Halo128Plan h3a, h3b, h4a, h4b, hPD;                  // 256-pixel halo tiles, streamed weights (conv_halo128.cu)
   bool use_halo128 = false;
   bool nms_large = false;                               // DV_NMS_TILE=L / S: 128x64 or 64x32 NMS tiles (A/B)
+  bool nms_full = false;                                // DV_NMS_TILE=F: 64x32 tiles, every pool over the whole region (r01)
   bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
   int fuse1a_tc = 0;                                    // DV_SP_FUSE1A=2: conv1a on the tensor cores inside conv1b (conv_halo.cu FUSE == 2)
   bool fuse1a = false;                                  // DV_SP_FUSE1A=1: conv1a inside conv1b's producer (correct, but the
@@ -201,8 +202,9 @@ __global__ void k_softmax_d2s(const float* __restrict__ logits, int ld, float* _
 //   NmsCfgS: 64 x 32 tiles, 104 x 72 region (3.65x the tile), 75 KB, 320 threads, three CTAs per SM          (r01)
 //   NmsCfgL: 128 x 64 tiles, 168 x 104 region (2.13x the tile), 171 KB, 768 threads, one CTA per SM: 1.7x fewer
 //            region pixels per frame through the ten separable passes
-struct NmsCfgS { static constexpr int TW = 64, TH = 32, THREADS = 320, ROW_STRIP = 26, COL_STRIP = 24; };
-struct NmsCfgL { static constexpr int TW = 128, TH = 64, THREADS = 768, ROW_STRIP = 24, COL_STRIP = 26; };
+struct NmsCfgS { static constexpr int TW = 64, TH = 32, THREADS = 320, ROW_STRIP = 26, COL_STRIP = 24; static constexpr bool APRON = true; };
+struct NmsCfgF { static constexpr int TW = 64, TH = 32, THREADS = 320, ROW_STRIP = 26, COL_STRIP = 24; static constexpr bool APRON = false; };   // r01: full region in every pass
+struct NmsCfgL { static constexpr int TW = 128, TH = 64, THREADS = 768, ROW_STRIP = 24, COL_STRIP = 26; static constexpr bool APRON = false; };
 template <class C> struct NmsDims {
   static constexpr int RW = C::TW + 2 * NMS_HALO, RH = C::TH + 2 * NMS_HALO, RN = RW * RH;
   static constexpr int SMEM = RN * (2 * 4 + 2);
@@ -261,6 +263,61 @@ __device__ __forceinline__ void maxpool9(IN in, OUT out, float* T1) {
   __syncthreads();
 }
 
+// The same 9x9 max-pool restricted to the part of the region that can still influence the tile (NmsCfgS only, r02).
+// The five pools of simple_nms consume 4 pixels of apron each: pool k only has to be right on the region shrunk by
+// a = 4k pixels per side ([a, RH - a) x [a, RW - a)), and its row pass only on the rows the column pass reads
+// ([a - 4, RH - a + 4)).  Summed over the ten passes that is 42 k region pixels per tile instead of 74 k.  LR / LC are the
+// strip lengths of the row / column pass (chosen per pool so that the 320 threads stay busy; odd row-strip lengths keep
+// the strips of neighbouring lanes off the same banks).  Values outside the shrinking rectangle are stale but never read
+// by anything that reaches the tile.
+template <int L, class LD, class ST>
+__device__ __forceinline__ void strip_max9_b(LD ld, ST st, int p0, int n, int hi) {
+  float v[L + 8];
+#pragma unroll
+  for (int i = 0; i < L + 8; ++i) {
+    const int p = p0 + i - 4;
+    v[i] = (p >= 0 && p < n) ? ld(p) : -INFINITY;
+  }
+  float m2[L + 7];
+#pragma unroll
+  for (int i = 0; i < L + 7; ++i) m2[i] = fmaxf(v[i], v[i + 1]);
+  float m4[L + 5];
+#pragma unroll
+  for (int i = 0; i < L + 5; ++i) m4[i] = fmaxf(m2[i], m2[i + 2]);
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const float m8 = fmaxf(m4[i], m4[i + 4]);
+    if (p0 + i < hi) st(p0 + i, fmaxf(m8, v[i + 8]));
+  }
+}
+template <class C, int A, int LR, int LC, class IN, class OUT>
+__device__ __forceinline__ void maxpool9_apron(IN in, OUT out, float* T1) {
+  constexpr int RW = NmsDims<C>::RW, RH = NmsDims<C>::RH;
+  constexpr int W = RW - 2 * A, H = RH - 2 * A;              // output rectangle
+  constexpr int NS = (W + LR - 1) / LR, ROWS = H + 8;        // row pass: strips per row, rows [A - 4, RH - A + 4)
+  constexpr int NC = (H + LC - 1) / LC;                      // column pass: strips per column
+  static_assert(A >= 4 && ROWS * NS <= C::THREADS && W * NC <= C::THREADS, "one strip per thread");
+  {
+    const int t = threadIdx.x;
+    if (t < ROWS * NS) {
+      const int row = A - 4 + t / NS, sp = t % NS;
+      const int base = row * RW;
+      strip_max9_b<LR>([&](int p) { return in(base + p); }, [&](int p, float m) { T1[base + p] = m; }, A + sp * LR, RW,
+                       RW - A);
+    }
+  }
+  __syncthreads();
+  {
+    const int t = threadIdx.x;
+    if (t < W * NC) {
+      const int sp = t / W, col = A + t % W;
+      strip_max9_b<LC>([&](int p) { return T1[p * RW + col]; }, [&](int p, float m) { out(p * RW + col, m); },
+                       A + sp * LC, RH, RH - A);
+    }
+  }
+  __syncthreads();
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::THREADS) k_nms_select(const float* __restrict__ smap, float* __restrict__ nms_out,
                                                     unsigned long long* __restrict__ cand, int* __restrict__ cand_cnt,
@@ -284,24 +341,34 @@ __global__ void __launch_bounds__(C::THREADS) k_nms_select(const float* __restri
   __syncthreads();
   // export/superpoint.py:52-66 simple_nms: max_mask = scores == max_pool(scores); two rounds of
   // supp = max_pool(mask) > 0; supp_scores = where(supp, 0, scores); mask |= (supp_scores == max_pool(supp_scores)) & ~supp
-  maxpool9<C>([&](int i) { return S[i]; },
-           [&](int i, float m) {
-             const float v = S[i];
-             MM[i] = (v != NEG) && (v == m);
-           },
-           T1);
-  for (int round = 0; round < 2; ++round) {
-    maxpool9<C>([&](int i) { return MM[i] ? 1.f : 0.f; }, [&](int i, float m) { SUPP[i] = m > 0.f; }, T1);
-    maxpool9<C>(
-        [&](int i) {
-          const float v = S[i];
-          return (v == NEG) ? NEG : (SUPP[i] ? 0.f : v);
-        },
-        [&](int i, float m) {
-          const float v = S[i];
-          if (v != NEG && !SUPP[i] && v == m) MM[i] = 1;
-        },
-        T1);
+  auto in_s = [&](int i) { return S[i]; };
+  auto out_m0 = [&](int i, float m) {
+    const float v = S[i];
+    MM[i] = (v != NEG) && (v == m);
+  };
+  auto in_m = [&](int i) { return MM[i] ? 1.f : 0.f; };
+  auto out_supp = [&](int i, float m) { SUPP[i] = m > 0.f; };
+  auto in_ss = [&](int i) {
+    const float v = S[i];
+    return (v == NEG) ? NEG : (SUPP[i] ? 0.f : v);
+  };
+  auto out_m = [&](int i, float m) {
+    const float v = S[i];
+    if (v != NEG && !SUPP[i] && v == m) MM[i] = 1;
+  };
+  if constexpr (C::APRON) {
+    // shrinking rectangles: each pool is evaluated only where it can still reach the tile (see maxpool9_apron)
+    maxpool9_apron<C, 4, 25, 22>(in_s, out_m0, T1);
+    maxpool9_apron<C, 8, 18, 19>(in_m, out_supp, T1);
+    maxpool9_apron<C, 12, 17, 12>(in_ss, out_m, T1);
+    maxpool9_apron<C, 16, 13, 10>(in_m, out_supp, T1);
+    maxpool9_apron<C, 20, 9, 8>(in_ss, out_m, T1);
+  } else {
+    maxpool9<C>(in_s, out_m0, T1);
+    for (int round = 0; round < 2; ++round) {
+      maxpool9<C>(in_m, out_supp, T1);
+      maxpool9<C>(in_ss, out_m, T1);
+    }
   }
   for (int i = threadIdx.x; i < NMS_TW * NMS_TH; i += blockDim.x) {
     const int ty = i / NMS_TW, tx = i - ty * NMS_TW;
@@ -591,8 +658,9 @@ int sp_init(Engine* e) {
     DV_TRY(plan_gemm(&s->pDb, s->aPD + 256, 512, (int)P8, s->wDb, 256, 256, 256, ed));
   }
   DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select<NmsCfgS>, cudaFuncAttributeMaxDynamicSharedMemorySize, NmsDims<NmsCfgS>::SMEM));
+  DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select<NmsCfgF>, cudaFuncAttributeMaxDynamicSharedMemorySize, NmsDims<NmsCfgF>::SMEM));
   DV_CUDA_OK(cudaFuncSetAttribute(k_nms_select<NmsCfgL>, cudaFuncAttributeMaxDynamicSharedMemorySize, NmsDims<NmsCfgL>::SMEM));
-  { const char* env = getenv("DV_NMS_TILE"); s->nms_large = env ? env[0] == 'L' : DV_NMS_DEFAULT_LARGE; }
+  { const char* env = getenv("DV_NMS_TILE"); s->nms_large = env ? env[0] == 'L' : DV_NMS_DEFAULT_LARGE; s->nms_full = env && env[0] == 'F'; }
   // debug views
   e->dbg["gray"] = {s->gray, (int64_t)H * W, 0};
   e->dbg[s->use_halo ? "conv1a_blocked" : "conv1a"] = {s->a1a, (int64_t)H * W * 64, 1};
@@ -698,6 +766,9 @@ static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
   DV_CUDA_OK(cudaMemsetAsync(s->cand_cnt, 0, sizeof(int) * b, e->st));
   if (s->nms_large)
     k_nms_select<NmsCfgL><<<dim3(cdiv(W8, NmsCfgL::TW), cdiv(H8, NmsCfgL::TH), b), NmsCfgL::THREADS, NmsDims<NmsCfgL>::SMEM, e->st>>>(
+        smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
+  else if (s->nms_full)
+    k_nms_select<NmsCfgF><<<dim3(cdiv(W8, NmsCfgF::TW), cdiv(H8, NmsCfgF::TH), b), NmsCfgF::THREADS, NmsDims<NmsCfgF>::SMEM, e->st>>>(
         smap, nms_out, s->cand, s->cand_cnt, H8, W8, e->cfg.border, e->cfg.det_thresh);
   else
     k_nms_select<NmsCfgS><<<dim3(cdiv(W8, NmsCfgS::TW), cdiv(H8, NmsCfgS::TH), b), NmsCfgS::THREADS, NmsDims<NmsCfgS>::SMEM, e->st>>>(
