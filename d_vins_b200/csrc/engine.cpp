@@ -536,6 +536,7 @@ dv_status dv_dbg_read(dv_engine* h, const char* name, float* dst, int64_t capaci
   const Engine::Dbg& d = it->second;
   if (count) *count = d.n;
   if (!dst) return DV_OK;
+  DV_TRY(sp_dbg_refresh(e, name));
   if (capacity < d.n) { set_error("dv_dbg_read: capacity too small"); return DV_ERR_CAPACITY; }
   if (d.dtype == 0 || d.dtype == 2) {
     DV_CUDA_OK(cudaMemcpyAsync(dst, d.p, (size_t)d.n * 4, cudaMemcpyDeviceToHost, e->st));

@@ -207,6 +207,7 @@ void f16_to_f32(const __half* src, float* dst, int64_t n, cudaStream_t st);
 int sp_init(Engine* e);                       // sp.cu
 void sp_free(Engine* e);
 int sp_run_encoder(Engine* e, int b);         // gray -> conv1a .. heads (logits + dense descriptor map)
+int sp_dbg_refresh(Engine* e, const char* name);     // lazily produced debug tensors ("gray")
 int sp_run_detect(Engine* e, int b);          // softmax/d2s, NMS, select, sample -> device results
 int sp_run_describe(Engine* e, int b, const float* d_kpts, const int* d_n, int cap, float* d_desc);
 void sp_device_results(Engine* e, int** kpts, float** kpts_f, float** scores, int** n, float** desc, float** re_kpts,

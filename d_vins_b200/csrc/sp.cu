@@ -28,6 +28,7 @@ struct SpNet {
   HaloPlan h1b, h2a, h2b;                               // weights-stationary halo kernels for the 64->64 layers
   Halo128Plan h3a, h3b, h4a, h4b, hPD;                  // 256-pixel halo tiles, streamed weights (conv_halo128.cu)
   bool use_halo128 = false;
+  bool gray_valid = false;                              // the fp32 gray frame of the current batch exists
   bool nms_large = false;                               // DV_NMS_TILE=L / S: 128x64 or 64x32 NMS tiles (A/B)
   bool nms_full = false;                                // DV_NMS_TILE=F: 64x32 tiles, every pool over the whole region (r01)
   bool use_halo = true;                                 // DV_SP_HALO=0: generic tap-per-TMA kernel (debug toggle)
@@ -694,6 +695,8 @@ int sp_run_encoder(Engine* e, int b) {
   if (!s) { set_error("SuperPoint not initialised (engine created without weights)"); return DV_ERR_INVALID; }
   StageScope sc(e, ST_SP_CONV);
   e->image_acquire();
+  // host-side state (graph replays do not run the enqueue code): is the fp32 gray frame produced on this path?
+  s->gray_valid = !(s->use_halo && s->fuse1a_tc && e->img_ch == 1);
   if (b == 1) {
     // per-keyframe latency path: 13 launches replayed as one CUDA graph; the frame-buffer events stay outside of it.
     // The frame pointer is a kernel argument baked into the graph and frames are double-buffered: one graph per buffer.
@@ -708,11 +711,13 @@ static int sp_enqueue_encoder(Engine* e, int b, bool release_inline) {
   SpNet* s = e->sp;
   const int H = e->H, W = e->W;
   const int64_t npix = (int64_t)b * H * W;
-  k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
+  // 1-channel frames: conv1a runs on the tensor cores inside conv1b, straight from the u8 frame (3-channel frames
+  // go through the fp64 gray mix of k_gray and the separate conv1a kernel); the fp32 gray frame is then not needed at
+  // all (92 MB per 64 frames) and is only produced on demand for dv_dbg_read("gray") (sp_dbg_refresh)
+  const bool tc1a_path = s->use_halo && s->fuse1a_tc && e->img_ch == 1;
+  if (!tc1a_path) k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
   if (s->use_halo) {
-    // 1-channel frames: conv1a runs on the tensor cores inside conv1b, straight from the u8 frame (3-channel frames
-    // go through the fp64 gray mix of k_gray and the separate conv1a kernel)
-    const bool tc1a = s->fuse1a_tc && e->img_ch == 1;
+    const bool tc1a = tc1a_path;
     if (!s->fuse1a && !tc1a) {
       k_conv1a_blocked<<<dim3(cdiv(W, 128), cdiv(H, CONV1A_ROWS), b), 256, 0, e->st>>>(s->gray, s->w1a, s->b1a, s->a1a, H, W);
       DV_CUDA_OK(cudaGetLastError());
@@ -776,6 +781,17 @@ static int run_post(Engine* e, int b, const float* smap, float* nms_out) {
   k_topk<<<b, 1024, 0, e->st>>>(s->cand, s->cand_cnt, H8 * W8, K, W8, s->kpts, s->kpts_f, s->scores, s->n_kpts);
   DV_CUDA_OK(cudaGetLastError());
   DV_LAUNCHED(e, 2);
+  return DV_OK;
+}
+
+// dv_dbg_read("gray"): the pre-processed frame is skipped on the tensor-core conv1a path; produce it on demand
+int sp_dbg_refresh(Engine* e, const char* name) {
+  SpNet* s = e->sp;
+  if (!s || strcmp(name, "gray") != 0 || s->gray_valid || e->cur_b <= 0) return DV_OK;
+  const int64_t npix = (int64_t)e->cur_b * e->H * e->W;
+  k_gray<<<(unsigned)cdiv64(npix, 256), 256, 0, e->st>>>(e->d_img, s->gray, npix, e->img_ch);
+  DV_CUDA_OK(cudaGetLastError());
+  s->gray_valid = true;
   return DV_OK;
 }
 
