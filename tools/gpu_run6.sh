@@ -4,10 +4,11 @@ B="python bench.py --steps 5 --warmup 3 --no-latency --no-cpu-baseline"
 run() { name=$1; shift; env "$@" timeout 300 $B > gpurun_out/sweep_$name.json 2> gpurun_out/sweep_$name.err; python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/sweep_$name.json")); print("$name", round(d["value"]), {k:round(v,3) for k,v in d["stage_ms_per_round"].items()})
+    d=json.load(open("gpurun_out/sweep_$name.json")); print("$name", round(d["value"]), {k:round(v,3) for k,v in d["stage_ms_per_round"].items()}, round(d["roofline"]["frac"],3))
 except Exception as ex: print("$name FAILED", ex)
 PY
 tail -n 2 gpurun_out/sweep_$name.err
 }
-run nmsF DV_NMS_TILE=F
-run nmsS DV_NMS_TILE=S
+run h64pair0 DV_SP_HALO64_PAIR=0
+run h64pair1 DV_SP_HALO64_PAIR=1
+run h64pair3 DV_SP_HALO64_PAIR=3
