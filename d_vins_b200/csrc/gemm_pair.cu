@@ -129,12 +129,109 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
         tc_commit_pair(&acc_full[a], 3);
       }
     }
+  } else if (UW == 16) {
+    if constexpr (UW == 16 && F32 && F16) {
+      // -------------------------------------------------------------- epilogue with residual PREFETCH (ffn.3 signature:
+      // fp32 residual in, fp32 + fp16 out, possibly in place).  16-column units: per warp a residual box R and separate
+      // output boxes S (fp32) / Hb (fp16) - 5 KB - so the residual of unit u + 1 (or of the next tile's unit 0) is
+      // requested as soon as unit u's has been read into registers and travels under unit u's TMEM read, arithmetic and
+      // stores.  With the in-place boxes of the wider units the load could only be issued after the previous store had
+      // finished reading the box, and its full HBM latency sat on every unit's critical path.
+      const int e = warp - 2;
+      const int q = warp & 3;                    // TMEM lane quarter
+      const int h0 = e >> 2;                     // column half [128 h0, +128) of the slab: eight units of 16 columns
+      uint8_t* R = smem + c.sb32_off + e * 4096;
+      uint8_t* S = R + 2048;
+      uint8_t* Hb = smem + c.sb16_off + e * 1024;
+      uint64_t* rb = &rbar[e];
+      const uint32_t sw64 = (((uint32_t)lane >> 1) & 3u);        // SWIZZLE_64B: 16-byte chunk ^= (row >> 1) & 3
+      uint32_t rphase = 0;
+      auto issue_res = [&](int st, int u) {
+        const int r0 = st * 256 + (int)rank * 128 + q * 32;
+        if (r0 < p.M && lane == 0) {
+          mbar_arrive_expect_tx(rb, 2048u);
+          tma_load_2d(R, &tmR32, rb, col_base + h0 * 128 + u * 16, r0);
+        }
+      };
+      int it = 0;
+      if (j0 < c.s_tiles) issue_res(j0, 0);
+      for (int st = j0; st < c.s_tiles; st += c.group, ++it) {
+        const int a = it & 1;
+        const int row0 = st * 256 + (int)rank * 128 + q * 32;
+        const bool active = row0 < p.M;                  // warp-uniform
+        mbar_wait(&acc_full[a], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + h0 * 128);
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+          const int lcol = h0 * 128 + u * 16;
+          float v[16];
+          if (active) {
+            mbar_wait(rb, rphase);
+            rphase ^= 1u;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 t = *reinterpret_cast<const float4*>(R + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw64) << 4));
+              v[g * 4 + 0] = t.x; v[g * 4 + 1] = t.y; v[g * 4 + 2] = t.z; v[g * 4 + 3] = t.w;
+            }
+          }
+          __syncwarp();                                  // every lane has read R: the next box may land in it
+          if (u < 7) issue_res(st, u + 1);
+          else if (st + c.group < c.s_tiles) issue_res(st + c.group, 0);
+          if (active) {
+            uint32_t r[16];
+            tmem_ld16(taddr + u * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&sbias[lcol + g * 4]);   // broadcast
+              v[g * 4 + 0] += __uint_as_float(r[g * 4 + 0]) + b4.x;
+              v[g * 4 + 1] += __uint_as_float(r[g * 4 + 1]) + b4.y;
+              v[g * 4 + 2] += __uint_as_float(r[g * 4 + 2]) + b4.z;
+              v[g * 4 + 3] += __uint_as_float(r[g * 4 + 3]) + b4.w;
+            }
+            if (ep.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+          }
+          if (u == 7) tc_fence_before();                 // last TMEM read of this accumulator buffer
+          if (lane == 0) bulk_wait_read0();              // the previous stores finished READING S / Hb
+          __syncwarp();
+          if (active) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<float4*>(S + (uint32_t)lane * 64u + ((((uint32_t)g) ^ sw64) << 4)) =
+                  make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              __align__(16) __half2 hv[4];
+#pragma unroll
+              for (int x = 0; x < 4; ++x) hv[x] = __floats2half2_rn(v[g * 8 + 2 * x], v[g * 8 + 2 * x + 1]);
+              *reinterpret_cast<uint4*>(Hb + (uint32_t)lane * 32u + (uint32_t)g * 16u) = *reinterpret_cast<const uint4*>(hv);
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (u == 7) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));
+            if (active) {
+              tma_store_2d(&tmO32, S, col_base + lcol, row0);
+              tma_store_2d(&tmO16, Hb, col_base + lcol, row0);
+              bulk_commit();
+            }
+          }
+        }
+      }
+      if (lane == 0) bulk_wait0();
+    }
   } else if (warp - 2 < c.epi_warps) {
     // ------------------------------------------------------------------ epilogue: 8 (or 4) warps per CTA
     const int e = warp - 2;
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    constexpr int NCI = UW / 32;               // 32-column TMEM loads per unit
-    constexpr uint32_t B32_BYTES = UW * 32 * 4, B16_BYTES = UW * 32 * 2;
+    constexpr int UWG = UW < 32 ? 32 : UW;     // (the 16-column prefetch epilogue above never reaches this branch)
+    constexpr int NCI = UWG / 32;              // 32-column TMEM loads per unit
+    constexpr uint32_t B32_BYTES = UWG * 32 * 4, B16_BYTES = UWG * 32 * 2;
     const int nh = c.epi_warps == 8 ? 1 : 2;   // UW = 64: column halves this warp walks per 128-column sub-tile
     const int h0 = c.epi_warps == 8 ? (e >> 2) : 0;
     uint8_t* b32 = smem + c.sb32_off + e * B32_BYTES;
@@ -308,13 +405,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 static int g_sms_pair = 148;
 static int g_use_pair = 2;                             // DV_GEMM_PAIR: 0 off, 1 all eligible shapes, 2 only K > 256
 static int g_pair_narrow = 1;                          // DV_GEMM_PAIR_NARROW: 0 never, 1 fp32 + fp16 outputs, 2 fp16-only too
+static int g_pair_prefetch = 1;                        // DV_GEMM_PAIR_PREFETCH=0: no 16-column residual-prefetch epilogue (A/B)
 static constexpr uint32_t PAIR_SMEM_MAX = 232448;      // 227 KB opt-in limit per CTA
 
 int gemm_pair_init() {
   { const char* e = getenv("DV_GEMM_PAIR"); if (e) g_use_pair = atoi(e); }
   { const char* e = getenv("DV_GEMM_PAIR_NARROW"); if (e) g_pair_narrow = atoi(e); }
+  { const char* e = getenv("DV_GEMM_PAIR_PREFETCH"); if (e) g_pair_prefetch = atoi(e); }
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_pair_kernel<true, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_MAX));
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_pair_kernel<true, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_MAX));
+  DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_pair_kernel<true, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_MAX));
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_pair_kernel<true, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_MAX));
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_pair_kernel<false, true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_MAX));
   DV_CUDA_OK(cudaFuncSetAttribute(umma_gemm_pair_kernel<false, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_MAX));
@@ -339,6 +439,28 @@ static bool pair_config(const GemmPlan& pl, long m_tiles, PairCfg* c) {
   // 32-column units need 64-byte fp16 boxes: no fp16 residual (never used with fp32 + fp16 outputs) and no rotary
   // with fp16-only outputs kept simple; rope_cols handled for both widths
   const bool narrow_ok = !ep.res16 && ((f32 && f16 && g_pair_narrow >= 1) || (!f32 && f16 && g_pair_narrow >= 2));
+  // ffn.3 signature (fp32 residual in, fp32 + fp16 out, no fp16 residual / rotary): 16-column units with residual prefetch
+  if (g_pair_prefetch && f32 && f16 && ep.res32 && ep.out32 && ep.out16 && !ep.res16 && !ep.rope16 && !ep.rope_cs) {
+    const uint32_t staging = 8u * 4096u + 8u * 1024u;
+    if (wbytes + staging + fixed + 2u * 16384u <= PAIR_SMEM_MAX) {
+      int stages = (int)((PAIR_SMEM_MAX - wbytes - staging - fixed) / 16384u);
+      if (stages > 8) stages = 8;
+      c->epi_warps = 8; c->uw = 16;
+      c->n_slabs = p.N / 256;
+      if (c->n_slabs > pairs) return false;
+      c->s_tiles = (int)((m_tiles + 1) / 2);
+      c->group = pairs / c->n_slabs;
+      if (c->group > c->s_tiles) c->group = c->s_tiles;
+      c->stages = stages;
+      c->a_off = wbytes;
+      c->sb32_off = c->a_off + (uint32_t)stages * 16384u;
+      c->sb16_off = c->sb32_off + 8u * 4096u;
+      c->bar_off = c->sb16_off + 8u * 1024u;
+      c->bias_off = c->bar_off + 512u;
+      c->smem_bytes = c->bias_off + 1024u + 1024u;
+      return true;
+    }
+  }
   for (int cand = 0; cand < 3; ++cand) {                    // (8 warps, 64), (8 warps, 32), (4 warps, 64)
     const int epi = cand == 2 ? 4 : 8, uw = cand == 1 ? 32 : 64;
     if (uw == 32 && !narrow_ok) continue;
@@ -379,9 +501,10 @@ int launch_gemm_pair(const GemmPlan& pl, const GemmParams& p, long m_tiles, cuda
   const EpiParams& ep = p.epi;
   if (pl.staged_rows != p.M) {
     // exact row count: the TMA engine clips the last row tile, so rows >= M are neither read nor written
-    if (ep.out32) DV_RC(tmap_encode_rows(&pl.tmO32, ep.out32, 4, p.N, p.M, (long)ep.ld32 * 4, 32, 32));
+    const int w32 = c.uw == 16 ? 16 : 32;
+    if (ep.out32) DV_RC(tmap_encode_rows(&pl.tmO32, ep.out32, 4, p.N, p.M, (long)ep.ld32 * 4, w32, 32));
     if (ep.out16) DV_RC(tmap_encode_rows(&pl.tmO16, ep.out16, 2, p.N, p.M, (long)ep.ld16 * 2, c.uw, 32));
-    if (ep.res32) DV_RC(tmap_encode_rows(&pl.tmR32, ep.res32, 4, p.N, p.M, (long)ep.ldr32 * 4, 32, 32));
+    if (ep.res32) DV_RC(tmap_encode_rows(&pl.tmR32, ep.res32, 4, p.N, p.M, (long)ep.ldr32 * 4, w32, 32));
     if (ep.res16) DV_RC(tmap_encode_rows(&pl.tmR16, ep.res16, 2, p.N, p.M, (long)ep.ldr16 * 2, c.uw, 32));
     pl.staged_rows = p.M;
   }
@@ -398,7 +521,11 @@ int launch_gemm_pair(const GemmPlan& pl, const GemmParams& p, long m_tiles, cuda
 #define DV_PAIR_LAUNCH(F32_, F16_, UW_)                                                                              \
   DV_CUDA_OK(launch_pdl(umma_gemm_pair_kernel<F32_, F16_, UW_>, dim3(grid), dim3(320), c.smem_bytes, st, pl.tmA, pl.tmB, \
                         pl.tmO32, pl.tmO16, pl.tmR32, pl.tmR16, pd, c))
-  if (f32 && f16) { if (c.uw == 32) DV_PAIR_LAUNCH(true, true, 32); else DV_PAIR_LAUNCH(true, true, 64); }
+  if (f32 && f16) {
+    if (c.uw == 16) DV_PAIR_LAUNCH(true, true, 16);
+    else if (c.uw == 32) DV_PAIR_LAUNCH(true, true, 32);
+    else DV_PAIR_LAUNCH(true, true, 64);
+  }
   else if (f32) DV_PAIR_LAUNCH(true, false, 64);
   else { if (c.uw == 32) DV_PAIR_LAUNCH(false, true, 32); else DV_PAIR_LAUNCH(false, true, 64); }
 #undef DV_PAIR_LAUNCH

@@ -298,8 +298,8 @@ int tmap_encode_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t*
 int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long cols, long rows, long pitch_bytes,
                      int box_cols, int box_rows) {
   if (!g_encode || (reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0 ||
-      (box_cols * elem_bytes != 128 && box_cols * elem_bytes != 64)) {
-    set_error("tmap_encode_rows: base / pitch must be 16-byte aligned and the box 128 or 64 bytes wide");
+      (box_cols * elem_bytes != 128 && box_cols * elem_bytes != 64 && box_cols * elem_bytes != 32)) {
+    set_error("tmap_encode_rows: base / pitch must be 16-byte aligned and the box 128, 64 or 32 bytes wide");
     return DV_ERR_INVALID;
   }
   cuuint64_t d[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -308,7 +308,8 @@ int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long col
   cuuint32_t es[2] = {1, 1};
   CUresult r = g_encode(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        box_cols * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        box_cols * elem_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : box_cols * elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -9,6 +9,5 @@ except Exception as ex: print("$name FAILED", ex)
 PY
 tail -n 2 gpurun_out/sweep_$name.err
 }
-run h64pair0 DV_SP_HALO64_PAIR=0
-run h64pair1 DV_SP_HALO64_PAIR=1
-run h64pair3 DV_SP_HALO64_PAIR=3
+run pref0 DV_GEMM_PAIR_PREFETCH=0
+run pref1 DV_GEMM_PAIR_PREFETCH=1
