@@ -603,15 +603,15 @@ def main():
         flop = 2.0 * H * W * 64 * (576 + 9) * b
         achieved = flop / (k_ms * 1e-3) / 1e12 if probe_n else None
         # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-        # (480x752, 32 frames/launch: 11.7 MB read = the u8 frames, 315.8 MB written = the pooled fp16 output; the
-        # algorithmic bytes are 11.6 + 369.6 MB, part of the output was still in L2 at kernel end), scaled by pixels
-        traffic = (11.669504e6 + 315.845376e6) * b / 32.0 * (H * W) / (480.0 * 752.0)
+        # (r02, 480x752, 64 frames/launch: 23.3 MB read = the u8 frames, 686.6 MB written = the pooled fp16 output; the
+        # algorithmic bytes are 23.1 + 739.2 MB, part of the output was still in L2 at kernel end), scaled by batch / pixels
+        traffic = (23.271e6 + 686.55e6) * b / 64.0 * (H * W) / (480.0 * 752.0)
         roofline = {"kernel": "conv3x3_halo64_kernel<2> (SuperPoint conv1a 1->64 on the tensor cores inside conv1b 3x3 "
                               "64->64 + ReLU + 2x2 max-pool, halo-tile implicit GEMM, %d frames/launch)" % b,
                     "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                     "frac": (achieved / tf_peak) if achieved else None, "traffic": traffic,
-                    "traffic_source": "ncu --set full, profiles/r01_conv1a1b_fused_ncu_raw_selected.txt (scaled by "
-                                      "batch/32 and pixel count)",
+                    "traffic_source": "ncu --set full, profiles/r02_kernels_ncu_selected.txt (conv3x3_halo64_kernel<2>, 64 "
+                                      "frames; scaled by batch/64 and pixel count)",
                     "peak_source": peak_src, "frac_of_burst_peak": (achieved / tf_burst) if achieved else None,
                     "avg_launch_ms": k_ms, "launches_timed": probe_n, "flop_per_launch": flop}
     else:
