@@ -40,57 +40,19 @@ struct Ffn0Params {
   const float *bias, *gamma, *beta;
 };
 
-// Packed fp32 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100): one issue slot for two lanes of work.  The epilogue of this
-// kernel is instruction-issue bound (ncu: 59 % of the issue slots, FMA pipe 33 %), and the exact GELU is ~15 dependent
-// fp32 operations per element: evaluated on (even, odd) column pairs it takes half the issue slots.  Each packed
-// operation rounds per lane exactly like its scalar counterpart, and the operation order is that of k_lg_ln_gelu (lg.cu).
-__device__ __forceinline__ unsigned long long pk(float2 a) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-  return r;
+__device__ __forceinline__ float ffn0_gelu_erf(float x) {      // the same Abramowitz-Stegun erf as k_lg_ln_gelu (lg.cu)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfc_z = poly * t * e;
+  const float half_x = 0.5f * x;
+  return x >= 0.f ? fmaf(-half_x, erfc_z, x) : half_x * erfc_z;
 }
-__device__ __forceinline__ float2 upk(unsigned long long r) {
-  float2 a;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
-  return a;
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
-  return upk(d);
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
-  return upk(d);
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
-  return upk(d);
-}
-__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
-// exact (erf) GELU of two values: Abramowitz-Stegun 7.1.26 on bare MUFU rcp / ex2, as gelu_erf() in lg.cu
-__device__ __forceinline__ float2 ffn0_gelu_erf2(float2 x) {
-  const float2 z = mul2(make_float2(fabsf(x.x), fabsf(x.y)), bc2(0.70710678118654752f));
-  const float2 den = fma2(bc2(0.3275911f), z, bc2(1.0f));
-  const float2 ez = mul2(mul2(bc2(-1.4426950408889634f), z), z);
-  float2 t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(ez.x));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(ez.y));
-  float2 poly = fma2(bc2(1.061405429f), t, bc2(-1.453152027f));
-  poly = fma2(poly, t, bc2(1.421413741f));
-  poly = fma2(poly, t, bc2(-0.284496736f));
-  poly = fma2(poly, t, bc2(0.254829592f));
-  const float2 erfc_z = mul2(mul2(poly, t), e);
-  const float2 half_x = mul2(x, bc2(0.5f));
-  const float2 pos = fma2(mul2(x, bc2(-0.5f)), erfc_z, x);       // x >= 0: 0.5 x (2 - erfc)
-  const float2 neg = mul2(half_x, erfc_z);                       // x <  0: 0.5 x erfc
-  return make_float2(x.x >= 0.f ? pos.x : neg.x, x.y >= 0.f ? pos.y : neg.y);
-}
-
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
     lg_ffn0_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmO16, const Ffn0Params p, int s_tiles, int n_clusters) {
@@ -206,22 +168,21 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + hq * 64);
       // ---- sweep 1: row sum / sum of squares of (acc + bias) rounded to fp16
-      float2 s1p = make_float2(0.f, 0.f), s2p = make_float2(0.f, 0.f);      // (even, odd) column partial sums
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         uint32_t r[32];
         tmem_ld32(taddr + ci * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          const float2 b2 = *reinterpret_cast<const float2*>(&spar[hq * 64 + ci * 32 + g * 2]);   // broadcast
-          const float2 v = add2(make_float2(__uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1])), b2);
-          const float2 f = __half22float2(__floats2half2_rn(v.x, v.y));
-          s1p = add2(s1p, f);
-          s2p = fma2(f, f, s2p);
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&spar[hq * 64 + ci * 32 + g * 4]);   // broadcast
+          const float2 f0 = __half22float2(__floats2half2_rn(__uint_as_float(r[g * 4 + 0]) + b4.x, __uint_as_float(r[g * 4 + 1]) + b4.y));
+          const float2 f1 = __half22float2(__floats2half2_rn(__uint_as_float(r[g * 4 + 2]) + b4.z, __uint_as_float(r[g * 4 + 3]) + b4.w));
+          s1 += (f0.x + f0.y) + (f1.x + f1.y);
+          s2 = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, s2))));
         }
       }
-      const float s1 = s1p.x + s1p.y, s2 = s2p.x + s2p.y;
       float2* pt = part + par * 512;                               // [4 column quarters][128 rows], double-buffered by tile
       pt[hq * 128 + row] = make_float2(s1, s2);
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // the four warps of this lane quarter
@@ -264,10 +225,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
             const float2 bb = *reinterpret_cast<const float2*>(&spar[cc]);
             const float2 gg = *reinterpret_cast<const float2*>(&spar[256 + cc]);
             const float2 be = *reinterpret_cast<const float2*>(&spar[512 + cc]);
-            const float2 v = add2(make_float2(__uint_as_float(r[g * 8 + 2 * x]), __uint_as_float(r[g * 8 + 2 * x + 1])), bb);
-            const float2 f = __half22float2(__floats2half2_rn(v.x, v.y));
-            const float2 y = ffn0_gelu_erf2(fma2(fma2(f, bc2(rstd), bc2(nmr)), gg, be));
-            hv[x] = __floats2half2_rn(y.x, y.y);
+            const float2 f = __half22float2(__floats2half2_rn(__uint_as_float(r[g * 8 + 2 * x]) + bb.x,
+                                                              __uint_as_float(r[g * 8 + 2 * x + 1]) + bb.y));
+            const float y0 = ffn0_gelu_erf(fmaf(fmaf(f.x, rstd, nmr), gg.x, be.x));
+            const float y1 = ffn0_gelu_erf(fmaf(fmaf(f.y, rstd, nmr), gg.y, be.y));
+            hv[x] = __floats2half2_rn(y0, y1);
           }
           // 64-byte rows, SWIZZLE_64B: 16-byte chunk ^= address bits [7:8] = (row >> 1) & 3
           *reinterpret_cast<uint4*>(b16 + (uint32_t)lane * 64u + ((((uint32_t)g) ^ (((uint32_t)lane >> 1) & 3u)) << 4)) =
