@@ -38,6 +38,7 @@ constexpr uint32_t F0_SMEM = F0_XBUF + 2048 + 1024;            // + alignment sl
 struct Ffn0Params {
   int M;                          // token rows
   const float *bias, *gamma, *beta;
+  long long* dbg;                 // DV_FFN0_DBG: cycle counters of one epilogue thread (diagnostics only)
 };
 
 __device__ __forceinline__ float ffn0_gelu_erf(float x) {      // the same Abramowitz-Stegun erf as k_lg_ln_gelu (lg.cu)
@@ -157,15 +158,19 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
     const uint32_t xbuf_partner = mapa_u32(smem_u32(xbuf), partner);
     const uint32_t xbar_partner = mapa_u32(smem_u32(xbar), partner);
     const int bar_id = 1 + q;
+    const bool dbgt = p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0;
+    long long d_acc = 0, d_s1 = 0, d_x = 0, d_s2 = 0;
     int it = 0;
     for (int st = cluster; st < s_tiles; st += n_clusters, ++it) {
       const int a = it & 1, par = it & 1;
+      const long long t0 = dbgt ? clock64() : 0;
       const int row0 = st * 256 + (int)rhalf * 128 + q * 32;     // first row of this warp
       const bool active = row0 < p.M;                            // warp-uniform (partials are exchanged regardless)
       // this quarter's 32 partner partials (8 bytes each) arrive as asynchronous remote stores that complete on xbar
       if (hq == 0 && lane == 0) mbar_arrive_expect_tx(&xbar[par * 4 + q], 256u);
       mbar_wait(&acc_full[a], (it >> 1) & 1);
       tc_fence_after();
+      const long long t1 = dbgt ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + hq * 64);
       // ---- sweep 1: row sum / sum of squares of (acc + bias) rounded to fp16
       float s1 = 0.f, s2 = 0.f;
@@ -183,6 +188,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
           s2 = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, s2))));
         }
       }
+      const long long t2 = dbgt ? clock64() : 0;
       float2* pt = part + par * 512;                               // [4 column quarters][128 rows], double-buffered by tile
       pt[hq * 128 + row] = make_float2(s1, s2);
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // the four warps of this lane quarter
@@ -202,6 +208,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
       const float var = fmaxf((c2 + px.y) * (1.f / 512.f) - mean * mean, 0.f);
       const float rstd = rsqrtf(var + 1e-5f);
       const float nmr = -mean * rstd;
+      const long long t3 = dbgt ? clock64() : 0;
       // ---- sweep 2: normalise, GELU, fp16 -> staging -> TMA store, 32 columns at a time
 #pragma unroll 1
       for (int u = 0; u < 2; ++u) {
@@ -242,7 +249,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(576, 1)
           bulk_commit();
         }
       }
+      if (dbgt) { const long long t4 = clock64(); d_acc += t1 - t0; d_s1 += t2 - t1; d_x += t3 - t2; d_s2 += t4 - t3; }
     }
+    if (dbgt) { p.dbg[0] = d_acc; p.dbg[1] = d_s1; p.dbg[2] = d_x; p.dbg[3] = d_s2; p.dbg[4] = it; }
     if (lane == 0) bulk_wait0();
   }
   // no CTA may exit (or free TMEM) while another can still signal its barriers / write its shared memory
@@ -297,9 +306,21 @@ int launch_lg_ffn0(const Ffn0Plan& pl, int rows, cudaStream_t st) {
   if (n_clusters > s_tiles) n_clusters = s_tiles;
   Ffn0Params p;
   p.M = rows; p.bias = pl.bias; p.gamma = pl.gamma; p.beta = pl.beta;
+  static long long* d_dbg = nullptr;
+  static const bool want_dbg = getenv("DV_FFN0_DBG") != nullptr;
+  if (want_dbg && !d_dbg) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+  p.dbg = want_dbg ? d_dbg : nullptr;
   DV_CUDA_OK(launch_pdl(lg_ffn0_kernel, dim3(4 * n_clusters), dim3(576), (size_t)F0_SMEM, st, pl.tmA, pl.tmB, pl.tmO16, p,
                         s_tiles, n_clusters));
   DV_CUDA_OK(cudaGetLastError());
+  if (want_dbg) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[ffn0 dbg] rows %d clusters %d | CTA 0 warp 2: tiles %lld, cycles per tile: accumulator wait %lld, sweep 1 %lld, "
+            "combine + DSMEM exchange %lld, sweep 2 %lld\n", rows, n_clusters, h[4], h[0] / (h[4] ? h[4] : 1), h[1] / (h[4] ? h[4] : 1),
+            h[2] / (h[4] ? h[4] : 1), h[3] / (h[4] ? h[4] : 1));
+  }
   return DV_OK;
 }
 
