@@ -36,7 +36,8 @@ struct GemmParams {
   int M, N, K;          // M rows actually computed (set at launch), N output columns, K reduction length
   int num_kb;           // K blocks of 64
   int n_tiles;
-  int conv;             // 0: plain row-major A; 1: 3x3 pad-1 conv over NHWC A
+  int conv;             // 0: plain row-major A; 1: 3x3 pad-1 conv over NHWC A (H, W = OUTPUT size)
+  int cstride = 1;      // conv: spatial stride 1 or 2 (stride 2: the TMA box samples every other input pixel)
   int H, W, cin, cin_blocks, tw_log2, tiles_w, tiles_h;
   EpiParams epi;
   // batched mode (persistent kernel only): tile -> (batch b, m_tile, n_tile); operands are row windows of the same two
@@ -64,8 +65,9 @@ struct GemmPlan {
 int plan_gemm(GemmPlan* pl, const __half* A, int lda, int M_cap, const __half* B, int ldb, int N, int K,
               const EpiParams& epi, int bn = 0);
 // x NHWC [n_cap, H, W, cin] fp16 (cin % 64 == 0), w [cout, 9*cin] fp16 with k = (r*3+s)*cin + c.
+// stride 2: H, W are the INPUT size; the output is (H/2) x (W/2) (pad 1, torchvision ResNet downsampling blocks)
 int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin, const __half* w, int cout,
-                 const EpiParams& epi);
+                 const EpiParams& epi, int stride = 1);
 // rows = M (plain) or number of images (conv).
 int launch_gemm(const GemmPlan& pl, int rows, cudaStream_t st);
 // batched: `desc` device array of {a_row_off, b_row_off, m, n}; max_m / max_n bound the tile grid (fp32 output only)

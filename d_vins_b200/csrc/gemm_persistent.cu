@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_persist_kernel(const __grid_
             const int tap = kb / p.cin_blocks;
             const int cb = kb - tap * p.cin_blocks;
             const int r3 = tap / 3, s3 = tap - r3 * 3;
-            tma_load_4d(sA, &tmA, &full[s], cb * 64, w0 + s3 - 1, h0 + r3 - 1, img);
+            tma_load_4d(sA, &tmA, &full[s], cb * 64, w0 * p.cstride + s3 - 1, h0 * p.cstride + r3 - 1, img);
             kB = tap * p.cin + cb * 64;
           } else {
             tma_load_2d(sA, &tmA, &full[s], kb * 64, tx.a_row + m_tile * 128);

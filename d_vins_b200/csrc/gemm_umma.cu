@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
           const int tap = kb / p.cin_blocks;
           const int cb = kb - tap * p.cin_blocks;
           const int r3 = tap / 3, s3 = tap - r3 * 3;
-          tma_load_4d(sA, &tmA, &full[s], cb * 64, w0 + s3 - 1, h0 + r3 - 1, img);
+          tma_load_4d(sA, &tmA, &full[s], cb * 64, w0 * p.cstride + s3 - 1, h0 * p.cstride + r3 - 1, img);
           kB = tap * p.cin + cb * 64;
         } else {
           tma_load_2d(sA, &tmA, &full[s], kb * 64, m_tile * 128);
@@ -323,8 +323,10 @@ int tmap_encode_rows(CUtensorMap* tm, const void* base, int elem_bytes, long col
 }
 
 static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr) {
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) es[i] = elem_strides[i];
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
     set_error("tensor map base not 16-byte aligned");
     return DV_ERR_INVALID;
@@ -380,12 +382,17 @@ int plan_gemm(GemmPlan* pl, const __half* A, int lda, int M_cap, const __half* B
   return encode_weights(pl, B, ldb, N, K);
 }
 
-int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin, const __half* w, int cout,
-                 const EpiParams& epi) {
+int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int Hin, int Win, int cin, const __half* w, int cout,
+                 const EpiParams& epi, int stride) {
   if (cin % 64) {
     set_error("plan_conv3x3: cin must be a multiple of 64");
     return DV_ERR_INVALID;
   }
+  if (stride != 1 && (stride != 2 || (Hin & 1) || (Win & 1) || epi.pool)) {
+    set_error("plan_conv3x3: stride must be 1, or 2 with even input size and no pooling");
+    return DV_ERR_INVALID;
+  }
+  const int H = Hin / stride, W = Win / stride;      // output size: the tiles and the epilogue walk output pixels
   pl->bn = pick_bn(cout, 0);
   pl->rows_cap = n_cap;
   GemmParams& p = pl->p;
@@ -394,7 +401,7 @@ int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin
   p.cin = cin; p.cin_blocks = cin / 64;
   p.num_kb = 9 * p.cin_blocks;
   p.n_tiles = cdiv(cout, pl->bn);
-  p.conv = 1; p.H = H; p.W = W;
+  p.conv = 1; p.H = H; p.W = W; p.cstride = stride;
   // tile = TH x TW pixels, TH*TW = 128.  Pooling needs TW <= 16 (2x2 partners inside one warp) and even TH, TW.
   int best = -1; long best_cost = 0;
   for (int l = (epi.pool ? 1 : 0); l <= (epi.pool ? 4 : 7); ++l) {
@@ -407,10 +414,14 @@ int plan_conv3x3(GemmPlan* pl, const __half* x, int n_cap, int H, int W, int cin
   p.tiles_h = cdiv(H, 128 >> best);
   p.epi = epi;
   p.M = 0;
-  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_cap};
-  cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)W * cin * 2, (cuuint64_t)H * W * cin * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(1 << best), (cuuint32_t)(128 >> best), 1};
-  int rc = encode(&pl->tmA, x, 4, dims, strides, box);
+  // the tap operand of a TH x TW output tile is a box over the INPUT whose traversal stride is the convolution's stride:
+  // boxDim counts un-strided positions (stride * T), the box delivers ceil(boxDim / stride) = T elements per dimension;
+  // coordinates outside the image are zero-filled (= the convolution's padding)
+  cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)n_cap};
+  cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)Win * cin * 2, (cuuint64_t)Hin * Win * cin * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)(stride << best), (cuuint32_t)(stride * (128 >> best)), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  int rc = encode(&pl->tmA, x, 4, dims, strides, box, es);
   if (rc) return rc;
   return encode_weights(pl, w, 9 * cin, cout, 9 * cin);
 }

@@ -33,6 +33,7 @@ struct MixNet {
   std::vector<GemmPlan> plans;
   StemPlan stem;                       // 7x7/2 stem as one implicit GEMM with in-kernel im2col (stem_conv.cu)
   bool fused_stem = true;              // DV_MIX_STEM=0: im2col kernel + GEMM (A/B)
+  bool strided_conv = true;            // DV_MIX_S2CONV=0: im2col kernel + GEMM for the two 3x3/2 convolutions (A/B)
   std::vector<HaloPlan> hplans;        // layer1's 64->64 3x3 convs run on the weights-stationary halo kernel
   std::vector<std::function<int(Engine*, int)>> ops;
   int n_launch = 0;
@@ -382,9 +383,10 @@ int mix_init(Engine* e) {
     m->n_launch++;
     return DV_OK;
   };
-  auto add_conv = [&](const __half* x, int Hh, int Ww, int cin, const __half* Wt, int cout, const EpiParams& ep) -> int {
+  auto add_conv = [&](const __half* x, int Hh, int Ww, int cin, const __half* Wt, int cout, const EpiParams& ep,
+                      int stride = 1) -> int {
     m->plans.emplace_back();
-    DV_TRY(plan_conv3x3(&m->plans.back(), x, B, Hh, Ww, cin, Wt, cout, ep));
+    DV_TRY(plan_conv3x3(&m->plans.back(), x, B, Hh, Ww, cin, Wt, cout, ep, stride));
     const int idx = (int)m->plans.size() - 1;
     m->ops.push_back([idx](Engine* en, int b) { return launch_gemm(en->mix->plans[idx], b, en->st); });
     m->n_launch++;
@@ -396,6 +398,7 @@ int mix_init(Engine* e) {
   };
 
   { const char* env = getenv("DV_MIX_CHUNK"); m->chunk = env ? atoi(env) : DV_MIX_CHUNK_DEFAULT; }
+  { const char* env = getenv("DV_MIX_S2CONV"); m->strided_conv = !(env && env[0] == '0'); }
   const std::string pre = "mix.backbone.model.";
   // ---- pre-processing + stem
   m->ops.push_back([](Engine* en, int b) {
@@ -465,6 +468,9 @@ int mix_init(Engine* e) {
         m->n_launch++;
       } else if (stride == 1) {
         DV_TRY(add_conv(m->t1, Hin, Hin, planes, w2, planes, epi16(m->t2, planes, b2, 1)));
+      } else if (m->strided_conv) {
+        // 3x3 / 2: implicit GEMM whose tap boxes sample every other input pixel (TMA traversal stride 2) - no im2col matrix
+        DV_TRY(add_conv(m->t1, Hin, Hin, planes, w2, planes, epi16(m->t2, planes, b2, 1), 2));
       } else {
         const int C = planes, Hi = Hin, Ho = Hout;
         m->ops.push_back([C, Hi, Ho](Engine* en, int b) {
