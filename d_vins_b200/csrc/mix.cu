@@ -186,32 +186,66 @@ __global__ void k_maxpool3s2(const __half* __restrict__ x, __half* __restrict__ 
   reinterpret_cast<uint4*>(out)[i] = *reinterpret_cast<uint4*>(m);
 }
 
-// [B, P, C] fp16 (NHWC feature map) -> [B, C, P] fp32 (mixer state), tiled through shared memory
-__global__ void k_transpose_h2f(const __half* __restrict__ in, float* __restrict__ out, int P, int C) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int p = p0 + r, c = c0 + threadIdx.x;
-    tile[r][threadIdx.x] = (p < P && c < C) ? __half2float(in[((int64_t)b * P + p) * C + c]) : 0.f;
+// [B, P, C] fp16 (NHWC feature map) -> [B, C, P] fp32 (mixer state), tiled through shared memory.
+// Tile = 64 channels x 80 positions (P = 400 = 5 x 80): 16-byte loads along the channels (128 contiguous bytes per
+// position), 16-byte stores along the positions (320 contiguous bytes per channel).  The 32 x 32 scalar version moved
+// 157 MB per 64 frames at 2.5 TB/s.
+#define TR_C 64
+#define TR_P 80
+__global__ void __launch_bounds__(256) k_transpose_h2f(const __half* __restrict__ in, float* __restrict__ out, int P, int C) {
+  __shared__ float tile[TR_C][TR_P + 1];
+  const int b = blockIdx.z, p0 = blockIdx.x * TR_P, c0 = blockIdx.y * TR_C;
+  for (int i = threadIdx.x; i < TR_P * (TR_C / 8); i += 256) {
+    const int pl = i >> 3, c8 = i & 7;
+    const int p = p0 + pl;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (p < P) v = __ldg(reinterpret_cast<const uint4*>(in + ((int64_t)b * P + p) * C + c0 + c8 * 8));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h2[j]);
+      tile[c8 * 8 + 2 * j][pl] = f.x;
+      tile[c8 * 8 + 2 * j + 1][pl] = f.y;
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int c = c0 + r, p = p0 + threadIdx.x;
-    if (c < C && p < P) out[((int64_t)b * C + c) * P + p] = tile[threadIdx.x][r];
+  for (int i = threadIdx.x; i < TR_C * (TR_P / 4); i += 256) {
+    const int cl = i / (TR_P / 4), p4 = i - cl * (TR_P / 4);
+    const int p = p0 + p4 * 4;
+    if (p + 3 < P) {
+      *reinterpret_cast<float4*>(out + ((int64_t)b * C + c0 + cl) * P + p) =
+          make_float4(tile[cl][p4 * 4], tile[cl][p4 * 4 + 1], tile[cl][p4 * 4 + 2], tile[cl][p4 * 4 + 3]);
+    } else {
+      for (int j = 0; j < 4 && p + j < P; ++j) out[((int64_t)b * C + c0 + cl) * P + p + j] = tile[cl][p4 * 4 + j];
+    }
   }
 }
-// [B, C, P] fp32 -> [B, P, C] fp16
-__global__ void k_transpose_f2h(const float* __restrict__ in, __half* __restrict__ out, int C, int P) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, c0 = blockIdx.x * 32, p0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int c = c0 + r, p = p0 + threadIdx.x;
-    tile[r][threadIdx.x] = (c < C && p < P) ? in[((int64_t)b * C + c) * P + p] : 0.f;
+// [B, C, P] fp32 -> [B, P, C] fp16: the mirror image (16-byte loads along the positions, 16-byte stores along the channels)
+__global__ void __launch_bounds__(256) k_transpose_f2h(const float* __restrict__ in, __half* __restrict__ out, int C, int P) {
+  __shared__ float tile[TR_C][TR_P + 1];
+  const int b = blockIdx.z, c0 = blockIdx.x * TR_C, p0 = blockIdx.y * TR_P;
+  for (int i = threadIdx.x; i < TR_C * (TR_P / 4); i += 256) {
+    const int cl = i / (TR_P / 4), p4 = i - cl * (TR_P / 4);
+    const int p = p0 + p4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p + 3 < P) {
+      v = *reinterpret_cast<const float4*>(in + ((int64_t)b * C + c0 + cl) * P + p);
+    } else {
+      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < 4 && p + j < P; ++j) t[j] = in[((int64_t)b * C + c0 + cl) * P + p + j];
+      v = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    tile[cl][p4 * 4] = v.x; tile[cl][p4 * 4 + 1] = v.y; tile[cl][p4 * 4 + 2] = v.z; tile[cl][p4 * 4 + 3] = v.w;
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int p = p0 + r, c = c0 + threadIdx.x;
-    if (p < P && c < C) out[((int64_t)b * P + p) * C + c] = __float2half_rn(tile[threadIdx.x][r]);
+  for (int i = threadIdx.x; i < TR_P * (TR_C / 8); i += 256) {
+    const int pl = i >> 3, c8 = i & 7;
+    const int p = p0 + pl;
+    if (p >= P) continue;
+    __align__(16) __half2 hv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hv[j] = __floats2half2_rn(tile[c8 * 8 + 2 * j][pl], tile[c8 * 8 + 2 * j + 1][pl]);
+    *reinterpret_cast<uint4*>(out + ((int64_t)b * P + p) * C + c0 + c8 * 8) = *reinterpret_cast<const uint4*>(hv);
   }
 }
 
@@ -516,7 +550,7 @@ int mix_init(Engine* e) {
   const __half* feat = x;   // [B,400,1024] NHWC
   // ---- aggregator
   m->ops.push_back([feat](Engine* en, int b) {
-    k_transpose_h2f<<<dim3(cdiv(400, 32), 1024 / 32, b), dim3(32, 8), 0, en->st>>>(feat, en->mix->x32, 400, 1024);
+    k_transpose_h2f<<<dim3(cdiv(400, TR_P), 1024 / TR_C, b), 256, 0, en->st>>>(feat, en->mix->x32, 400, 1024);
     return (int)DV_OK;
   });
   m->n_launch++;
@@ -547,7 +581,7 @@ int mix_init(Engine* e) {
     DV_TRY(add_gemm(m->h16, 400, B * 1024, dw2, 400, 400, 400, ep, 1024));
   }
   m->ops.push_back([](Engine* en, int b) {
-    k_transpose_f2h<<<dim3(1024 / 32, cdiv(400, 32), b), dim3(32, 8), 0, en->st>>>(en->mix->x32, en->mix->xT16, 1024, 400);
+    k_transpose_f2h<<<dim3(1024 / TR_C, cdiv(400, TR_P), b), 256, 0, en->st>>>(en->mix->x32, en->mix->xT16, 1024, 400);
     return (int)DV_OK;
   });
   m->n_launch++;
