@@ -276,6 +276,22 @@ class Engine:
         self.last_match_status = ko.copy()
         return [(ma[i, :max(ko[i], 0)], ms[i, :max(ko[i], 0)]) for i in range(b)]
 
+    def batch_match_begin(self, query_ids, old_ids, query_part=0, old_part=2, cap=None):
+        """Queue the LightGlue pass of a round and return; collect with batch_match_end() - meanwhile the next round may be
+        uploaded and extracted (its kernels queue behind the match)."""
+        q = np.ascontiguousarray(query_ids, dtype=np.int64); o = np.ascontiguousarray(old_ids, dtype=np.int64)
+        b = q.shape[0]; cap = cap or self.cfg.max_vio
+        self._mp = (b, int(cap), q, o)
+        _chk(_lib.dv_batch_match_begin(self._h, b, _ptr(q, C.c_int64), _ptr(o, C.c_int64), int(query_part), int(old_part), int(cap)))
+
+    def batch_match_end(self):
+        b, cap, _, _ = self._mp
+        ma = np.zeros((b, cap, 2), np.int32); ms = np.zeros((b, cap), np.float32); ko = np.zeros((b,), np.int32)
+        _chk(_lib.dv_batch_match_end(self._h, _ptr(ma, C.c_int32), _ptr(ms, C.c_float), _ptr(ko, C.c_int32)))
+        self._mp = None
+        self.last_match_status = ko.copy()
+        return [(ma[i, :max(ko[i], 0)], ms[i, :max(ko[i], 0)]) for i in range(b)]
+
     def batch_match_sp(self, query_ids, old_ids):
         """SuperPoint-vs-SuperPoint pair match (BASELINE config 2)."""
         return self.batch_match_ex(query_ids, old_ids, 1, 1, self.cfg.max_kpts)

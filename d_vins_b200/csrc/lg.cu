@@ -83,6 +83,7 @@ struct LgNet {
   // staging for the host-vector API
   float *st_k = nullptr, *st_d = nullptr, *h_st_k = nullptr, *h_st_d = nullptr;   // [2*segcap,2], [2*segcap,256]
   int* h_out_i = nullptr; float* h_out_f = nullptr;
+  cudaEvent_t ev_fetch = nullptr;      // results of the batched match in flight have landed in h_out_*
   std::map<std::pair<int, int>, GraphCache> graphs;     // P == 1 launch sequences by (m, n)
 };
 
@@ -806,6 +807,7 @@ int lg_init(Engine* e) {
 }
 
 void lg_free(Engine* e) {
+  if (e->lg && e->lg->ev_fetch) cudaEventDestroy(e->lg->ev_fetch);
   delete e->lg;
   e->lg = nullptr;
 }
@@ -978,7 +980,9 @@ int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float*
 
 // All pairs of a batched match in three strided D2H copies and ONE synchronisation (the per-pair version cost two
 // stream synchronisations per pair: ~1 ms of idle GPU per 32-pair round).  slot[p] = caller-side index of pair p.
-int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out) {
+// Split in two so that the copies can be queued right behind the kernels (lg_fetch_batch_begin) and collected later
+// (lg_fetch_batch_end: waits for the event, unpacks the pinned staging buffers) - dv_batch_match_begin / _end.
+int lg_fetch_batch_begin(Engine* e, int P, int cap) {
   LgNet* g = e->lg;
   const int SC = g->segcap;
   if (cap > SC) cap = SC;
@@ -990,7 +994,19 @@ int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches,
                                cudaMemcpyDeviceToHost, e->st));
   DV_CUDA_OK(cudaMemcpy2DAsync(h_s, sizeof(float) * cap, g->mscores, sizeof(float) * SC, sizeof(float) * cap, P,
                                cudaMemcpyDeviceToHost, e->st));
-  DV_CUDA_OK(cudaStreamSynchronize(e->st));
+  if (!g->ev_fetch) DV_CUDA_OK(cudaEventCreateWithFlags(&g->ev_fetch, cudaEventDisableTiming));
+  DV_CUDA_OK(cudaEventRecord(g->ev_fetch, e->st));
+  return DV_OK;
+}
+
+int lg_fetch_batch_end(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out) {
+  LgNet* g = e->lg;
+  const int SC = g->segcap;
+  if (cap > SC) cap = SC;
+  const int* h_m = g->h_out_i;
+  const int* h_k = g->h_out_i + (size_t)P * cap * 2;
+  const float* h_s = g->h_out_f;
+  DV_CUDA_OK(cudaEventSynchronize(g->ev_fetch));
   for (int p = 0; p < P; ++p) {
     const int k = h_k[p], i = slot[p];
     if (k > cap) { set_error("lg_fetch_batch: output capacity too small"); return DV_ERR_CAPACITY; }
@@ -999,6 +1015,11 @@ int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches,
     k_out[i] = k;
   }
   return DV_OK;
+}
+
+int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out) {
+  DV_TRY(lg_fetch_batch_begin(e, P, cap));
+  return lg_fetch_batch_end(e, P, cap, slot, matches, mscores, k_out);
 }
 
 }  // namespace dv

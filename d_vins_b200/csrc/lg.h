@@ -26,6 +26,8 @@ struct AttnJobU { int q_row, nq, k_row, nk, q_col, k_col, v_col, pad; };
 // in several chunks is fetched with ONE lg_fetch_batch at the end.
 int lg_run(Engine* e, int P, const LgSeg* segs, const std::function<int()>* after_load = nullptr, int out_base = 0);
 int lg_fetch_batch(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out);
+int lg_fetch_batch_begin(Engine* e, int P, int cap);      // queue the result copies behind the match kernels
+int lg_fetch_batch_end(Engine* e, int P, int cap, const int* slot, int32_t* matches, float* mscores, int32_t* k_out);
 int lg_fetch(Engine* e, int p, int cap, int32_t* matches, float* mscores, float* mk0, float* mk1, int32_t* k_out);
 
 }  // namespace dv

@@ -54,6 +54,10 @@ struct Store {
   int *d_meta_all = nullptr, *h_meta_all = nullptr;         // gathered [world*b,4]
   int *d_hdr_all = nullptr, *h_hdr_all = nullptr;           // dv_store_sync: gathered headers [world, slots, 4]
   // seqlock verification of remote reads: per pair {peer header pointer, expected id} -> flag
+  // dv_batch_match_begin .. dv_batch_match_end: the pairs in flight
+  bool mp_pending = false;
+  int mp_b = 0, mp_cap = 0, mp_npull = 0;
+  std::vector<int> mp_kout, mp_which, mp_pull_pair;
   struct PullJob { const int* hdr; int lo, hi, pad; };
   PullJob *d_pull = nullptr, *h_pull = nullptr;             // [2B]
   int *d_pull_bad = nullptr, *h_pull_bad = nullptr;         // [2B]
@@ -524,23 +528,27 @@ dv_status dv_batch_match(dv_engine* h, int32_t b, const int64_t* query_ids, cons
                            matches, mscores, k_out);
 }
 
-dv_status dv_batch_match_ex(dv_engine* h, int32_t b, const int64_t* query_ids, const int64_t* old_ids, int32_t query_part,
-                            int32_t old_part, int32_t out_cap, int32_t* matches, float* mscores, int32_t* k_out) {
+dv_status dv_batch_match_begin(dv_engine* h, int32_t b, const int64_t* query_ids, const int64_t* old_ids,
+                               int32_t query_part, int32_t old_part, int32_t out_cap) {
   DV_CHECK_ENGINE(h);
   Engine* e = reinterpret_cast<Engine*>(h);
   Store* s = e->store;
   if (!e->lg) { set_error("dv_batch_match: engine created without weights"); return DV_ERR_INVALID; }
-  if (b < 1 || b > e->B || !query_ids || !old_ids || !matches || !mscores || !k_out || query_part < 0 || query_part > 2 ||
+  if (b < 1 || b > e->B || !query_ids || !old_ids || query_part < 0 || query_part > 2 ||
       old_part < 0 || old_part > 2 || out_cap < 1) { set_error("dv_batch_match: bad arguments"); return DV_ERR_INVALID; }
+  if (s->mp_pending) { set_error("dv_batch_match_begin: the previous match has not been collected (dv_batch_match_end)"); return DV_ERR_INVALID; }
+  std::vector<int>& k_out = s->mp_kout;          // per-pair status until dv_batch_match_end
+  k_out.assign((size_t)b, 0);
+  std::vector<int>& which = s->mp_which;
+  std::vector<int>& pull_pair = s->mp_pull_pair;
+  which.clear(); pull_pair.clear();
   const int V = out_cap, me = e->cfg.rank;
   auto part = [](const Loc& L, int which, int* first, int* count) {
     *first = which == DV_PART_WINDOW ? L.n_sp : 0;
     *count = which == DV_PART_WINDOW ? L.n_vio : which == DV_PART_SP ? L.n_sp : L.n_sp + L.n_vio;
   };
   std::vector<LgSeg> segs;
-  std::vector<int> which;
-  int n_pull = 0;
-  std::vector<int> pull_pair;            // index into `which` of every pair whose old keyframe is remote
+  int n_pull = 0;                        // pull_pair: index into `which` of every pair whose old keyframe is remote
   for (int i = 0; i < b; ++i) {
     k_out[i] = 0;
     // per-pair status: -1 = one of the two keyframes is not (or no longer) resident anywhere; the other pairs still run
@@ -574,7 +582,8 @@ dv_status dv_batch_match_ex(dv_engine* h, int32_t b, const int64_t* query_ids, c
     }
     which.push_back(i);
   }
-  if (which.empty()) return DV_OK;
+  s->mp_b = b; s->mp_cap = V; s->mp_npull = 0;
+  if (which.empty()) { s->mp_pending = true; return DV_OK; }
   std::function<int()> after_load = [&]() -> int {
     if (!n_pull) return DV_OK;
     DV_CUDA_OK(cudaMemcpyAsync(s->d_pull, s->h_pull, sizeof(Store::PullJob) * n_pull, cudaMemcpyHostToDevice, e->st));
@@ -590,11 +599,34 @@ dv_status dv_batch_match_ex(dv_engine* h, int32_t b, const int64_t* query_ids, c
   const int step = (lg_chunk > 0 && lg_chunk < Pn) ? lg_chunk : Pn;
   for (int p0 = 0; p0 < Pn; p0 += step)
     DV_TRY(lg_run(e, std::min(step, Pn - p0), segs.data() + 2 * p0, (n_pull && p0 + step >= Pn) ? &after_load : nullptr, p0));   // seqlock check after the LAST load
-  DV_TRY(lg_fetch_batch(e, (int)which.size(), V, which.data(), matches, mscores, k_out));
-  // a remote keyframe whose slot was being rewritten while it was read is reported like a non-resident one
-  for (int j = 0; j < n_pull; ++j)
-    if (s->h_pull_bad[j]) k_out[which[pull_pair[j]]] = -1;
+  s->mp_npull = n_pull;
+  DV_TRY(lg_fetch_batch_begin(e, (int)which.size(), V));               // result copies queued behind the kernels
+  s->mp_pending = true;
   return DV_OK;
+}
+
+dv_status dv_batch_match_end(dv_engine* h, int32_t* matches, float* mscores, int32_t* k_out) {
+  DV_CHECK_ENGINE(h);
+  Engine* e = reinterpret_cast<Engine*>(h);
+  Store* s = e->store;
+  if (!s->mp_pending) { set_error("dv_batch_match_end: no match in flight"); return DV_ERR_INVALID; }
+  if (!matches || !mscores || !k_out) { set_error("dv_batch_match_end: null output"); return DV_ERR_INVALID; }
+  s->mp_pending = false;
+  for (int i = 0; i < s->mp_b; ++i) k_out[i] = s->mp_kout[i];
+  if (s->mp_which.empty()) return DV_OK;
+  DV_TRY(lg_fetch_batch_end(e, (int)s->mp_which.size(), s->mp_cap, s->mp_which.data(), matches, mscores, k_out));
+  // a remote keyframe whose slot was being rewritten while it was read is reported like a non-resident one
+  for (int j = 0; j < s->mp_npull; ++j)
+    if (s->h_pull_bad[j]) k_out[s->mp_which[s->mp_pull_pair[j]]] = -1;
+  return DV_OK;
+}
+
+dv_status dv_batch_match_ex(dv_engine* h, int32_t b, const int64_t* query_ids, const int64_t* old_ids, int32_t query_part,
+                            int32_t old_part, int32_t out_cap, int32_t* matches, float* mscores, int32_t* k_out) {
+  if (!matches || !mscores || !k_out) { set_error("dv_batch_match: bad arguments"); return DV_ERR_INVALID; }
+  const dv_status rc = dv_batch_match_begin(h, b, query_ids, old_ids, query_part, old_part, out_cap);
+  if (rc != DV_OK) return rc;
+  return dv_batch_match_end(h, matches, mscores, k_out);
 }
 
 }  // extern "C"

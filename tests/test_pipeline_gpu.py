@@ -221,3 +221,32 @@ def test_config_validation(weights_file):
     for kw in (dict(max_vio=600), dict(max_kpts=1024, max_vio=64), dict(max_batch=8, store_capacity=4)):
         with pytest.raises(capi.DvError):
             capi.Engine(height=160, width=224, weights_path=weights_file, **kw)
+
+
+def test_match_begin_end_equals_synchronous_match(eng):
+    """dv_batch_match_begin / _end: the next round is uploaded and extracted between the two halves (its kernels queue
+    behind the match); the collected results equal the synchronous dv_batch_match of the same pairs, and a second begin
+    without an end is refused."""
+    from d_vins_b200 import capi
+    from oracle import synth
+    st = synth.Stream(480, 752, period=12, margin=64)
+    b = 4
+    vio = np.zeros((b, 160, 2), np.float32); nv = np.full((b,), 150, np.int32)
+    for i in range(b):
+        vio[i, :150] = synth.vio_points(150, 480, 752, 70 + i)
+    eng.bank_import(np.zeros((0, 512), np.float32))
+    ids0, ids1, ids2 = (np.arange(b, dtype=np.int64) + k * b + 1000 for k in range(3))
+    for ids, t0 in ((ids0, 0), (ids1, 4)):
+        eng.batch_upload(np.stack([st.frame(t0 + t) for t in range(b)]))
+        eng.batch_extract(vio, nv, ids)
+        eng.batch_commit(b)
+    ref = eng.batch_match(ids1, ids0)
+    eng.batch_match_begin(ids1, ids0)
+    with pytest.raises(capi.DvError):
+        eng.batch_match_begin(ids1, ids0)
+    eng.batch_upload(np.stack([st.frame(8 + t) for t in range(b)]))      # the next round, queued behind the match
+    eng.batch_extract(vio, nv, ids2)
+    got = eng.batch_match_end()
+    assert len(got) == len(ref) and sum(len(m) for m, _ in ref) > 0
+    for (m0, s0), (m1, s1) in zip(ref, got):
+        assert np.array_equal(m0, m1) and np.array_equal(s0, s1)
