@@ -22,6 +22,10 @@ struct MixNet {
   float d2i[6] = {0, 0, 0, 0, 0, 0};
   float *ln_g[4] = {}, *ln_b[4] = {};
   float *row_w = nullptr, *row_b = nullptr;
+  float *chanT = nullptr, *chan_b = nullptr;   // reordered tail: channel_proj weight transposed [1024][256] fp32, bias [256]
+  float* u32 = nullptr;                        // [B*1024, 2] row_proj applied to the mixer state
+  float row_wsum[2] = {0.f, 0.f};              // sum_p row_proj.weight[r, p]
+  bool reorder_tail = true;                    // DV_MIX_TAIL=0: transpose + channel_proj GEMM + row_proj kernel (A/B)
   // buffers
   __half* img16 = nullptr;      // [B,320,320,3]
   __half* col = nullptr;        // im2col scratch
@@ -329,6 +333,86 @@ __global__ void __launch_bounds__(1024) k_rowproj_norm(const float* __restrict__
   }
 }
 
+// Reordered aggregator tail (r02).  channel_proj (1024 -> 256 over the channels) and row_proj (400 -> 2 over the
+// positions) are both linear and act on different axes, so
+//   z[c', r] = sum_c Wc[c', c] * (sum_p Wr[r, p] * x[c, p])  +  bc[c'] * sum_p Wr[r, p]  +  br[r]
+// i.e. row_proj FIRST: one streaming pass over the fp32 mixer state (105 MB per 64 frames) leaves [1024, 2] per frame, and
+// channel_proj shrinks to a 256 x 1024 x 2 product per frame.  The [C,P] fp32 -> [P,C] fp16 transpose (157 MB), the
+// 400 x 256 x 1024 GEMM per frame and its fp32 output round trip disappear; the state is never rounded to fp16.
+// k_rowproj_x: one warp per (frame, channel) row of 400 floats, the row in registers (128-bit loads).
+__global__ void __launch_bounds__(256) k_rowproj_x(const float* __restrict__ x, const float* __restrict__ w,
+                                                   float* __restrict__ u, int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 2;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float4 w0[4], w1[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool in = lane + 32 * k < nv;
+    w0[k] = in ? __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w1[k] = in ? __ldg(reinterpret_cast<const float4*>(w + D) + lane + 32 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < nv) {
+        const float4 v = xr[lane + 32 * k];
+        a0 = fmaf(v.x, w0[k].x, fmaf(v.y, w0[k].y, fmaf(v.z, w0[k].z, fmaf(v.w, w0[k].w, a0))));
+        a1 = fmaf(v.x, w1[k].x, fmaf(v.y, w1[k].y, fmaf(v.z, w1[k].z, fmaf(v.w, w1[k].w, a1))));
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) *reinterpret_cast<float2*>(u + row * 2) = make_float2(a0, a1);
+  }
+}
+// k_chanproj_norm: one block per frame; thread (o, grp) sums channels [256 grp, +256) of output o for both rows
+// (coalesced rows of the transposed weight), shared-memory combine, bias terms, block-wide L2 norm, index o*2 + r.
+__global__ void __launch_bounds__(1024) k_chanproj_norm(const float* __restrict__ u, const float* __restrict__ wT,
+                                                        const float* __restrict__ bc, const float* __restrict__ br,
+                                                        float ws0, float ws1, float* __restrict__ out) {
+  __shared__ float2 us[1024];
+  __shared__ float part[4][256][2];
+  __shared__ float red[8];
+  const int b = blockIdx.x, o = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  us[threadIdx.x] = *reinterpret_cast<const float2*>(u + ((int64_t)b * 1024 + threadIdx.x) * 2);
+  __syncthreads();
+  float a0 = 0.f, a1 = 0.f;
+  const float* wp = wT + (int64_t)grp * 256 * 256 + o;
+#pragma unroll 8
+  for (int c = 0; c < 256; ++c) {
+    const float wv = __ldg(wp + (int64_t)c * 256);
+    const float2 uv = us[grp * 256 + c];
+    a0 = fmaf(wv, uv.x, a0);
+    a1 = fmaf(wv, uv.y, a1);
+  }
+  part[grp][o][0] = a0;
+  part[grp][o][1] = a1;
+  __syncthreads();
+  if (grp == 0) {
+    const float bo = bc[o];
+    a0 = ((part[0][o][0] + part[1][o][0]) + (part[2][o][0] + part[3][o][0])) + fmaf(bo, ws0, br[0]);
+    a1 = ((part[0][o][1] + part[1][o][1]) + (part[2][o][1] + part[3][o][1])) + fmaf(bo, ws1, br[1]);
+    float ss = a0 * a0 + a1 * a1;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    if ((o & 31) == 0) red[o >> 5] = ss;
+  }
+  __syncthreads();
+  if (grp == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+    out[(int64_t)b * 512 + o * 2 + 0] = a0 * inv;
+    out[(int64_t)b * 512 + o * 2 + 1] = a1 * inv;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 namespace {
 
@@ -398,6 +482,7 @@ int mix_init(Engine* e) {
   DV_TRY(e->alloc(&m->xT16, (size_t)B * 400 * 1024));
   DV_TRY(e->alloc(&m->y32, (size_t)B * 400 * 256));
   DV_TRY(e->alloc(&m->gdesc, (size_t)B * 512));
+  DV_TRY(e->alloc(&m->u32, (size_t)B * 1024 * 2));
   m->plans.reserve(128);
   m->hplans.reserve(8);
 
@@ -433,6 +518,7 @@ int mix_init(Engine* e) {
 
   { const char* env = getenv("DV_MIX_CHUNK"); m->chunk = env ? atoi(env) : DV_MIX_CHUNK_DEFAULT; }
   { const char* env = getenv("DV_MIX_S2CONV"); m->strided_conv = !(env && env[0] == '0'); }
+  { const char* env = getenv("DV_MIX_TAIL"); m->reorder_tail = !(env && env[0] == '0'); }
   const std::string pre = "mix.backbone.model.";
   // ---- pre-processing + stem
   m->ops.push_back([](Engine* en, int b) {
@@ -580,30 +666,53 @@ int mix_init(Engine* e) {
     EpiParams ep; ep.out32 = m->x32; ep.ld32 = 400; ep.res32 = m->x32; ep.ldr32 = 400; ep.bias = db2;
     DV_TRY(add_gemm(m->h16, 400, B * 1024, dw2, 400, 400, 400, ep, 1024));
   }
-  m->ops.push_back([](Engine* en, int b) {
-    k_transpose_f2h<<<dim3(1024 / TR_C, cdiv(400, TR_P), b), 256, 0, en->st>>>(en->mix->x32, en->mix->xT16, 1024, 400);
-    return (int)DV_OK;
-  });
-  m->n_launch++;
   {
     const HostTensor *wc = e->weight("mix.aggregator.channel_proj.weight"), *bc = e->weight("mix.aggregator.channel_proj.bias");
     const HostTensor *wr = e->weight("mix.aggregator.row_proj.weight"), *br = e->weight("mix.aggregator.row_proj.bias");
-    if (!wc || !bc || !wr || !br || wc->numel() != 256 * 1024 || wr->numel() != 800) {
+    if (!wc || !bc || !wr || !br || wc->numel() != 256 * 1024 || wr->numel() != 800 || bc->numel() != 256 || br->numel() != 2) {
       set_error("MixVPR weights: aggregator.channel_proj / row_proj");
       return DV_ERR_WEIGHTS;
     }
-    __half* dwc; float* dbc;
-    DV_TRY(add_w(wc->data, bc->data, &dwc, &dbc));
-    EpiParams ep; ep.out32 = m->y32; ep.ld32 = 256; ep.bias = dbc;
-    DV_TRY(add_gemm(m->xT16, 1024, B * 400, dwc, 1024, 256, 1024, ep, 400));
     DV_TRY(e->upload_f32(wr->data, &m->row_w));
     DV_TRY(e->upload_f32(br->data, &m->row_b));
-    m->ops.push_back([](Engine* en, int b) {
-      MixNet* mm = en->mix;
-      k_rowproj_norm<<<b, 1024, 0, en->st>>>(mm->y32, mm->row_w, mm->row_b, mm->gdesc + (size_t)mm->frame_off * 512, 400);
-      return (int)DV_OK;
-    });
-    m->n_launch++;
+    if (m->reorder_tail) {
+      // row_proj first, channel_proj on [1024, 2] (see k_rowproj_x)
+      std::vector<float> wT((size_t)1024 * 256);
+      for (int o = 0; o < 256; ++o)
+        for (int c = 0; c < 1024; ++c) wT[(size_t)c * 256 + o] = wc->data[(size_t)o * 1024 + c];
+      DV_TRY(e->upload_f32(wT, &m->chanT));
+      DV_TRY(e->upload_f32(bc->data, &m->chan_b));
+      for (int r = 0; r < 2; ++r) {
+        double acc = 0.0;
+        for (int p = 0; p < 400; ++p) acc += (double)wr->data[(size_t)r * 400 + p];
+        m->row_wsum[r] = (float)acc;
+      }
+      m->ops.push_back([](Engine* en, int b) {
+        MixNet* mm = en->mix;
+        const int64_t rows = (int64_t)b * 1024;
+        k_rowproj_x<<<(unsigned)std::min<int64_t>(cdiv64(rows, 8), 148 * 8), 256, 0, en->st>>>(mm->x32, mm->row_w, mm->u32, rows, 400);
+        k_chanproj_norm<<<b, 1024, 0, en->st>>>(mm->u32, mm->chanT, mm->chan_b, mm->row_b, mm->row_wsum[0], mm->row_wsum[1],
+                                                mm->gdesc + (size_t)mm->frame_off * 512);
+        return (int)DV_OK;
+      });
+      m->n_launch += 2;
+    } else {
+      m->ops.push_back([](Engine* en, int b) {
+        k_transpose_f2h<<<dim3(1024 / TR_C, cdiv(400, TR_P), b), 256, 0, en->st>>>(en->mix->x32, en->mix->xT16, 1024, 400);
+        return (int)DV_OK;
+      });
+      m->n_launch++;
+      __half* dwc; float* dbc;
+      DV_TRY(add_w(wc->data, bc->data, &dwc, &dbc));
+      EpiParams ep; ep.out32 = m->y32; ep.ld32 = 256; ep.bias = dbc;
+      DV_TRY(add_gemm(m->xT16, 1024, B * 400, dwc, 1024, 256, 1024, ep, 400));
+      m->ops.push_back([](Engine* en, int b) {
+        MixNet* mm = en->mix;
+        k_rowproj_norm<<<b, 1024, 0, en->st>>>(mm->y32, mm->row_w, mm->row_b, mm->gdesc + (size_t)mm->frame_off * 512, 400);
+        return (int)DV_OK;
+      });
+      m->n_launch++;
+    }
   }
   e->dbg["mix_img"] = {m->img16, (int64_t)320 * 320 * 3, 1};
   e->dbg["mix_feat"] = {feat, (int64_t)400 * 1024, 1};

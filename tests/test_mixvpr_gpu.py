@@ -56,3 +56,39 @@ def test_mixvpr_bgr_input(eng, all_weights):
     assert np.array_equal(pre, ref_pre.astype(np.float16).astype(np.float32))
     ref = omix.mixvpr(weights.sub(all_weights, "mix."), img)
     assert float(ref @ got) > parity.GLOBAL_COS_MIN
+
+
+def test_reordered_tail_matches_gemm_tail():
+    """The aggregator tail with row_proj applied first (k_rowproj_x + k_chanproj_norm, fp32 throughout; the default)
+    against the transpose + channel_proj GEMM + row_proj kernels (DV_MIX_TAIL=0) on the same frames: the two are the same
+    linear map evaluated in a different order, so the unit descriptors agree to fp16-operand precision."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.getcwd())
+import bench
+from d_vins_b200 import capi
+from oracle import synth
+e = capi.Engine(height=480, width=752, weights_path=bench.make_weights())
+out = []
+for seed in (synth.BASE_SEED, synth.BASE_SEED + 5):
+    e.frame_upload(synth.make_frame(480, 752, seed))
+    out.append(e.mix_describe().tolist())
+print(json.dumps(out))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, DV_MIX_TAIL=mode),
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.asarray(json.loads(r.stdout.strip().splitlines()[-1]), np.float32))
+    a, b = outs
+    assert a.shape == b.shape == (2, 512)
+    for x, y in zip(a, b):
+        assert float(x @ y) > 0.99999, float(x @ y)
+        assert np.abs(x - y).max() < 1e-3, np.abs(x - y).max()
