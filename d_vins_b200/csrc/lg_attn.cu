@@ -348,8 +348,17 @@ __device__ __forceinline__ float row_exchange(uint32_t col_own, uint32_t col_oth
 __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                                  const AttnItem* __restrict__ items, int n_items,
                                                                  __half* __restrict__ ctx, int ldo, float sl2,
-                                                                 long long* dbg) {
+                                                                 int flags, float grow_thr, long long* dbg) {
   pdl_trigger();
+  // DV_ATTN_DBG timeline capture (dbg[8] != 0): one thread per CTA stamps its phases into dbg[16 + 8 bid ..]
+  long long* dbgc = nullptr;
+  if (dbg && threadIdx.x == 64 && dbg[8] != 0) {
+    dbgc = dbg + 16 + (long long)blockIdx.x * 8;
+    unsigned long long gt; unsigned sm;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+    dbgc[0] = clock64(); dbgc[6] = (long long)gt; dbgc[7] = (long long)sm;
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   if ((int)(smem - smem_raw) > ALIGN_SLACK) __trap();
@@ -376,6 +385,7 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (dbgc) dbgc[1] = clock64();
   // index of this CTA's item in round r (-1: none; then no later round has one either); descriptors are constants
   // written by a host copy that precedes the whole LightGlue pass, so they may be read before the dependency wait
   auto item_idx = [&](int r) -> int {
@@ -393,6 +403,7 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
   AttnItem cur = {0, 0, 0, 0, 0, 0, 0, 0}, nxt = cur;
   load_item(idx, cur);
   pdl_wait();
+  if (dbgc) dbgc[2] = clock64();
 
   if (warp == 0) {
     if (elect_one_sync()) {
@@ -410,6 +421,19 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
           mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
           tma_load_2d(smem + OFF_K + s * TILE_BYTES, &tmQKV, &kv_full[s], cur.k_col, cur.k_row + j * 128);
           tma_load_2d(smem + OFF_V + s * TILE_BYTES, &tmQKV, &kv_full[s], cur.v_col, cur.k_row + j * 128);
+        }
+        // A/B switch (DV_ATTN_PREFETCH=1, off by default): pull the next item's Q and first two K/V chunks into L2 once
+        // every K/V load of this item is queued.  Item boundaries wait ~1.1 k clk for the next first S although its
+        // operands were requested a sweep earlier (DV_ATTN_DBG), but the prefetch changes nothing: the 4-6 k clk a TMA
+        // load takes under this kernel's load is L2 -> SM delivery (15 B/clk per SM with <= 128 KB in flight), not DRAM.
+        if ((flags & 1) && nidx >= 0) {
+          tma_prefetch_2d(&tmQKV, nxt.q_col, nxt.q_row);
+          tma_prefetch_2d(&tmQKV, nxt.k_col, nxt.k_row);
+          tma_prefetch_2d(&tmQKV, nxt.v_col, nxt.k_row);
+          if (nxt.nk > 128) {
+            tma_prefetch_2d(&tmQKV, nxt.k_col, nxt.k_row + 128);
+            tma_prefetch_2d(&tmQKV, nxt.v_col, nxt.k_row + 128);
+          }
         }
         cur = nxt; idx = nidx;
       }
@@ -460,7 +484,7 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
     const uint32_t y_own = tl + 194 + half, y_oth = tl + 194 + (half ^ 1);     // ... row sum
     const int bar_id = 1 + q;
     uint8_t* ptile = smem + OFF_P + half * TILE_BYTES + row * 128;             // this warp's P tile row
-    const bool dbgt = dbg && bid == 3 && warp == 2 && lane == 0;               // DV_ATTN_DBG: cycle counters of one thread
+    const bool dbgt = dbg && bid == 3 && warp == 4 && lane == 0;               // DV_ATTN_DBG: one thread of lane quarter 0 (always live)
     long long d_s = 0, d_o = 0, d_sw = 0, d_x = 0, d_item = 0, d_ch = 0, d_end = 0;
     int g = 0;
     for (int n = 0; idx >= 0; ++n) {
@@ -472,9 +496,11 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
       if (dbgt) d_item += 1;
       for (int j = 0; j < n_chunks; ++j, ++g) {
         const long long t0 = dbgt ? clock64() : 0;
+        if (dbgt && j == 0 && n > 0) dbg[14] += t0 - dbg[13];            // previous item's end -> this item's first wait
         mbar_wait(s_full, g & 1);
         tc_fence_after();
-        if (dbgt) { d_s += clock64() - t0; d_ch += 1; }
+        if (dbgt) { d_s += clock64() - t0; d_ch += 1; if (j == 0) dbg[15] += clock64() - t0; }
+        if (dbgc && g == 0) dbgc[3] = clock64();
         const int kbase = j * 128;
         const int ngrp = min(4, (cur.nk - kbase + 31) >> 5);   // 32-key groups holding valid keys (PV reads no further)
         if (!warp_live) {                                      // every row of this lane quarter is padding
@@ -535,8 +561,9 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
           const long long t3 = dbgt ? clock64() : 0;
           mx = fmaxf(mx, row_exchange(x_own, x_oth, mx, bar_id));
           if (dbgt) { const long long t4 = clock64(); d_o += t2 - t1; d_sw += t3 - t2; d_x += t4 - t3; }
-          const bool grow = (mx - m_run) * sl2 > 8.f;          // identical in both warps of the row
+          const bool grow = (mx - m_run) * sl2 > grow_thr;     // identical in both warps of the row
           if (__any_sync(0xffffffffu, grow)) {
+            const long long tr = dbgt ? clock64() : 0;
             float corr = 1.f;
             if (grow) { corr = ex2_approx((m_run - mx) * sl2); m_run = mx; l_run *= corr; }
             uint32_t r[32];
@@ -549,8 +576,10 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
             sum = 0.f;
             float unused = -INFINITY;
             sweep(m_run * sl2, sum, unused);
+            if (dbgt) { dbg[11] += 1; dbg[12] += clock64() - tr; }
           }
         } else {
+          const long long tf = dbgt ? clock64() : 0;
           float mx = -INFINITY;
 #pragma unroll 1
           for (int c = c0; c < c1; ++c) {
@@ -569,6 +598,7 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
           m_run = fmaxf(mx, row_exchange(x_own, x_oth, mx, bar_id));   // first chunk: the reference is its own maximum
           float unused = -INFINITY;
           sweep(m_run * sl2, sum, unused);
+          if (dbgt) dbg[9] += clock64() - tf;
         }
         l_run += sum;
         fence_proxy_async_smem();
@@ -582,6 +612,7 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
       mbar_wait(o_full, (g - 1) & 1);
       tc_fence_after();
       if (dbgt) d_end += clock64() - te;
+      const long long tp = dbgt ? clock64() : 0;
       if (warp_live) {
         const float l_tot = l_run + row_exchange(y_own, y_oth, l_run, bar_id);
         uint32_t r[32];
@@ -604,13 +635,22 @@ __global__ void __launch_bounds__(320, 2) lg_attn_persist_kernel(const __grid_co
         tc_fence_before();
       }
       cur = nxt; idx = nidx;
+      if (dbgt) { dbg[10] += clock64() - tp; dbg[13] = clock64(); }
     }
     if (dbgt) {
       dbg[0] += d_s; dbg[1] += d_o; dbg[2] += d_sw; dbg[3] += d_x; dbg[4] += d_ch; dbg[5] += d_item; dbg[6] += d_end;
     }
+    if (dbgc) dbgc[4] = clock64();
   }
   tc_fence_before();
   __syncthreads();
+  if (dbgc) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    dbgc[5] = clock64();
+    dbgc[6] = (long long)gt - dbgc[6];          // CTA lifetime in ns
+    dbg[16 + 8 * 2 * 148 * 4 + blockIdx.x] = (long long)gt;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -667,19 +707,67 @@ int launch_lg_attn_persist(const CUtensorMap& tm, const void* items, int n_items
   static long long* d_dbg = nullptr;
   static const bool want = getenv("DV_ATTN_DBG") != nullptr;       // diagnostics: cycle counters of one softmax thread
   static int calls = 0;
-  if (want && !d_dbg) { cudaMalloc(&d_dbg, 64); cudaMemset(d_dbg, 0, 64); }
+  constexpr int DBG_WORDS = 16 + 8 * 2 * 148 * 4 + 2 * 148 * 4;    // counters, per-CTA timeline [grid][8], end timestamps
+  if (want && !d_dbg) { cudaMalloc(&d_dbg, DBG_WORDS * 8); cudaMemset(d_dbg, 0, DBG_WORDS * 8); }
+  // timeline capture of two launches (a self- and a cross-attention of the third LightGlue pass)
+  const bool cap = want && (calls == 38 || calls == 39) && grid <= 2 * 148 * 4;
+  if (cap) { const long long one = 1; cudaMemcpyAsync(d_dbg + 8, &one, 8, cudaMemcpyHostToDevice, st); cudaStreamSynchronize(st); }
+  // DV_ATTN_PREFETCH=1: L2 prefetch of the next item's first tiles (measured: no gain - 3.83 vs 3.80 ms per 64 pairs - the
+  // loaded TMA latency is L2 -> SM delivery, not DRAM; off by default).  DV_ATTN_GROW: log2 of the growth of a row maximum
+  // over the scaling reference that triggers a rescale of O in TMEM (default 12: P <= 2^12 in fp16, whose range ends at
+  // 2^16; r02 A/B: 8 -> 12 = -0.06 ms per 64 pairs, every parity test unchanged)
+  static const int flags = [] { const char* e = getenv("DV_ATTN_PREFETCH"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const float grow_thr = [] { const char* e = getenv("DV_ATTN_GROW"); const float v = e ? (float)atof(e) : 12.f;
+                                     return v < 1.f ? 1.f : (v > 14.f ? 14.f : v); }();
   DV_CUDA_OK(launch_pdl(lg_attn_persist_kernel, dim3(grid), dim3(320), (size_t)SMEM_BYTES, st, tm,
                         reinterpret_cast<const AttnItem*>(items), n_items, ctx, ldo, scale * 1.4426950408889634f,
-                        want ? d_dbg : (long long*)nullptr));
+                        flags, grow_thr, want ? d_dbg : (long long*)nullptr));
   DV_CUDA_OK(cudaGetLastError());
-  if (want && ++calls % 18 == 0) {
-    long long h[8];
+  if (cap) {
     cudaStreamSynchronize(st);
-    cudaMemcpy(h, d_dbg, 64, cudaMemcpyDeviceToHost);
-    cudaMemset(d_dbg, 0, 64);
-    fprintf(stderr, "[attn dbg] CTA 3 warp 2 over 18 launches: chunks %lld items %lld | cycles/chunk: wait S %lld, wait O %lld, sweep %lld, "
-            "exchange %lld | item-end O wait %lld per item\n", h[4], h[5], h[0] / (h[4] ? h[4] : 1), h[1] / (h[4] ? h[4] : 1),
-            h[2] / (h[4] ? h[4] : 1), h[3] / (h[4] ? h[4] : 1), h[6] / (h[5] ? h[5] : 1));
+    std::vector<long long> h(DBG_WORDS);
+    cudaMemcpy(h.data(), d_dbg, DBG_WORDS * 8, cudaMemcpyDeviceToHost);
+    const long long zero = 0;
+    cudaMemcpy(d_dbg + 8, &zero, 8, cudaMemcpyHostToDevice);
+    const long long* ends = h.data() + 16 + 8 * 2 * 148 * 4;
+    long long end_min = ends[0], end_max = ends[0];
+    std::vector<long long> ph[6];
+    std::vector<int> per_sm(1024, 0);
+    for (int b = 0; b < grid; ++b) {
+      const long long* c = h.data() + 16 + 8 * b;
+      ph[0].push_back(c[1] - c[0]); ph[1].push_back(c[2] - c[1]); ph[2].push_back(c[3] - c[2]);
+      ph[3].push_back(c[4] - c[3]); ph[4].push_back(c[5] - c[4]); ph[5].push_back(c[6]);
+      end_min = std::min(end_min, ends[b]); end_max = std::max(end_max, ends[b]);
+      if (c[7] >= 0 && c[7] < 1024) per_sm[(int)c[7]]++;
+    }
+    long long start_min = ends[0] - (h.data() + 16)[6], start_max = start_min;
+    for (int b = 0; b < grid; ++b) {
+      const long long s0 = ends[b] - (h.data() + 16 + 8 * b)[6];
+      start_min = std::min(start_min, s0); start_max = std::max(start_max, s0);
+    }
+    int sm_hist[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int v : per_sm) sm_hist[v < 7 ? v : 7]++;
+    auto q = [](std::vector<long long>& v, double f) { std::sort(v.begin(), v.end()); return v[(size_t)(f * (v.size() - 1))]; };
+    fprintf(stderr, "[attn timeline] launch %d: grid %d items %d | kernel span %lld ns (first CTA start -> last CTA end), starts spread %lld ns, "
+            "ends spread %lld ns | SMs holding 0/1/2/3+ CTAs: %d/%d/%d/%d\n", calls, grid, n_items, end_max - start_min, start_max - start_min,
+            end_max - end_min, sm_hist[0], sm_hist[1], sm_hist[2], sm_hist[3] + sm_hist[4] + sm_hist[5] + sm_hist[6] + sm_hist[7]);
+    const char* nm[6] = {"setup (clk)", "pdl wait (clk)", "first S (clk)", "item loop (clk)", "exit barrier (clk)", "CTA lifetime (ns)"};
+    for (int k2 = 0; k2 < 6; ++k2)
+      fprintf(stderr, "[attn timeline]   %-18s min %lld  p10 %lld  median %lld  p90 %lld  max %lld\n", nm[k2], q(ph[k2], 0.0), q(ph[k2], 0.1),
+              q(ph[k2], 0.5), q(ph[k2], 0.9), q(ph[k2], 1.0));
+  }
+  ++calls;
+  if (want && calls % 18 == 0) {
+    long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_dbg, 128, cudaMemcpyDeviceToHost);
+    cudaMemset(d_dbg, 0, 128);
+    const long long it = h[5] ? h[5] : 1;
+    fprintf(stderr, "[attn dbg] CTA 3 warp 4 over 18 launches: chunks %lld items %lld | cycles/chunk: wait S %lld, wait O %lld, sweep %lld, "
+            "exchange %lld | per item: first-chunk wait S %lld, first-chunk body %lld, item-end O wait %lld, epilogue %lld, item turn-over %lld | "
+            "rescales %lld (%lld clk each)\n", h[4], h[5], h[0] / (h[4] ? h[4] : 1), h[1] / (h[4] ? h[4] : 1),
+            h[2] / (h[4] ? h[4] : 1), h[3] / (h[4] ? h[4] : 1), h[15] / it, h[9] / it, h[6] / it, h[10] / it, h[14] / it,
+            h[11], h[12] / (h[11] ? h[11] : 1));
   }
   return DV_OK;
 }

@@ -58,6 +58,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// bring a tile into L2 only (no shared-memory destination, no barrier): hides the HBM latency of a later tma_load_2d
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
