@@ -1,6 +1,6 @@
-# r02 late A/B + validation bundle (ONE call): attention duo kernel (DV_ATTN_DUO) and reordered MixVPR tail (DV_MIX_TAIL)
-# against the previous defaults, then smoke / full GPU suite / headline bench / ncu launch list of bench.py with the
-# winning switches exported.  Everything lands in gpurun_out/r02b_*.
+# r02 late A/B + validation bundle (ONE call) as it ran for profiles/r02b_*: attention "duo" kernel (DV_ATTN_DUO - measured
+# slower and REMOVED afterwards, the variable is ignored now) and reordered MixVPR tail (DV_MIX_TAIL) against the previous
+# defaults, then smoke / full GPU suite / headline bench / ncu launch list of bench.py with the winning switches exported.
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 nvidia-smi -L
