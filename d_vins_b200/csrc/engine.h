@@ -81,6 +81,7 @@ struct Engine {
     if (next_pending) { cur_b = next_b; enc_done = det_done = mix_done = false; next_pending = false; }
   }
   bool enc_done = false, det_done = false, mix_done = false;
+  bool match_pending = false;   // dv_batch_match_begin .. _end: LightGlue's result staging buffers hold uncollected matches
 
   SpNet* sp = nullptr;
   MixNet* mix = nullptr;

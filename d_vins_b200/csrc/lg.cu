@@ -1036,6 +1036,7 @@ dv_status dv_lg_match(dv_engine* h, const float* kpts0, int32_t m, const float* 
   Engine* e = reinterpret_cast<Engine*>(h);
   LgNet* g = e->lg;
   if (!g) { set_error("dv_lg_match: engine created without weights"); return DV_ERR_INVALID; }
+  if (e->match_pending) { set_error("dv_lg_match: a batched match is in flight (collect it with dv_batch_match_end first)"); return DV_ERR_INVALID; }
   if (!kpts0 || !kpts1 || !desc0 || !desc1 || !matches || !mscores || !k_out) { set_error("dv_lg_match: null argument"); return DV_ERR_INVALID; }
   // engine profile of the reference: 10 <= kpts <= 1024 (README.md:180)
   if (m < 10 || n < 10 || m > e->cfg.lg_max_kpts || n > e->cfg.lg_max_kpts) { set_error("dv_lg_match: need 10 <= m,n <= lg_max_kpts"); return DV_ERR_INVALID; }
@@ -1062,6 +1063,7 @@ dv_status dv_dbg_match_extract(dv_engine* h, const float* L, int32_t m, int32_t 
   Engine* e = reinterpret_cast<Engine*>(h);
   LgNet* g = e->lg;
   if (!g) { set_error("dv_dbg_match_extract: engine created without weights"); return DV_ERR_INVALID; }
+  if (e->match_pending) { set_error("dv_dbg_match_extract: a batched match is in flight (dv_batch_match_end first)"); return DV_ERR_INVALID; }
   const int SC = g->segcap;
   if (!L || m < 1 || n < 1 || m > SC || n > SC) { set_error("dv_dbg_match_extract: bad shape"); return DV_ERR_INVALID; }
   DV_CUDA_OK(cudaMemcpy2DAsync(g->Lm, sizeof(float) * SC, L, sizeof(float) * n, sizeof(float) * n, m, cudaMemcpyHostToDevice, e->st));

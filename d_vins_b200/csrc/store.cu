@@ -583,7 +583,7 @@ dv_status dv_batch_match_begin(dv_engine* h, int32_t b, const int64_t* query_ids
     which.push_back(i);
   }
   s->mp_b = b; s->mp_cap = V; s->mp_npull = 0;
-  if (which.empty()) { s->mp_pending = true; return DV_OK; }
+  if (which.empty()) { s->mp_pending = true; e->match_pending = true; return DV_OK; }
   std::function<int()> after_load = [&]() -> int {
     if (!n_pull) return DV_OK;
     DV_CUDA_OK(cudaMemcpyAsync(s->d_pull, s->h_pull, sizeof(Store::PullJob) * n_pull, cudaMemcpyHostToDevice, e->st));
@@ -602,6 +602,7 @@ dv_status dv_batch_match_begin(dv_engine* h, int32_t b, const int64_t* query_ids
   s->mp_npull = n_pull;
   DV_TRY(lg_fetch_batch_begin(e, (int)which.size(), V));               // result copies queued behind the kernels
   s->mp_pending = true;
+  e->match_pending = true;
   return DV_OK;
 }
 
@@ -612,6 +613,7 @@ dv_status dv_batch_match_end(dv_engine* h, int32_t* matches, float* mscores, int
   if (!s->mp_pending) { set_error("dv_batch_match_end: no match in flight"); return DV_ERR_INVALID; }
   if (!matches || !mscores || !k_out) { set_error("dv_batch_match_end: null output"); return DV_ERR_INVALID; }
   s->mp_pending = false;
+  e->match_pending = false;
   for (int i = 0; i < s->mp_b; ++i) k_out[i] = s->mp_kout[i];
   if (s->mp_which.empty()) return DV_OK;
   DV_TRY(lg_fetch_batch_end(e, (int)s->mp_which.size(), s->mp_cap, s->mp_which.data(), matches, mscores, k_out));

@@ -161,7 +161,8 @@ dv_status dv_batch_match_ex(dv_engine* e, int32_t b, const int64_t* query_ids, c
  * returns; _end waits for them and fills matches [b, out_cap, 2] / mscores [b, out_cap] / k_out [b] of that call.  In
  * between the caller may upload and extract the NEXT round (dv_batch_upload / dv_batch_extract): its kernels queue right
  * behind the match, so the GPU never idles while the host collects results and prepares the next round (the reference
- * runs LightGlue synchronously inside findConnection, keyframe.cpp:583-632).  One match may be in flight. */
+ * runs LightGlue synchronously inside findConnection, keyframe.cpp:583-632).  One match may be in flight; until it is
+ * collected a second dv_batch_match* / dv_lg_match is refused (DV_ERR_INVALID) - they share the result staging buffers. */
 dv_status dv_batch_match_begin(dv_engine* e, int32_t b, const int64_t* query_ids, const int64_t* old_ids,
                                int32_t query_part, int32_t old_part, int32_t out_cap);
 dv_status dv_batch_match_end(dv_engine* e, int32_t* matches, float* mscores, int32_t* k_out);
