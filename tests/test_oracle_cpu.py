@@ -275,3 +275,23 @@ def test_knn_window_and_bruteforce_randomised():
         assert list(I[:len(order)]) == order
         assert all(i == -1 for i in I[len(order):]) and all(d == -np.inf for d in D[len(order):])
     check()
+
+
+def test_mixvpr_tail_reorder_identity(all_weights):
+    """The engine applies row_proj BEFORE channel_proj (mix.cu k_rowproj_x / k_chanproj_norm):
+    z[c', r] = sum_c Wc[c', c] (sum_p Wr[r, p] x[c, p]) + bc[c'] sum_p Wr[r, p] + br[r].  Check that identity against the
+    oracle's published order (channel_proj, then row_proj) on the oracle's own weights and a random mixer state."""
+    import torch
+    from oracle import weights
+    wm = weights.sub(all_weights, "mix.")
+    g = torch.Generator().manual_seed(11)
+    feat = torch.randn(1, 1024, 20, 20, generator=g, dtype=torch.float64)
+    t = lambda k: torch.as_tensor(np.asarray(wm[k]), dtype=torch.float64)
+    Wc, bc = t("aggregator.channel_proj.weight"), t("aggregator.channel_proj.bias")
+    Wr, br = t("aggregator.row_proj.weight"), t("aggregator.row_proj.bias")
+    x = feat.flatten(2)[0]                                     # [1024, 400]
+    z_pub = torch.nn.functional.linear(torch.nn.functional.linear(x.t(), Wc, bc).t(), Wr, br)   # [256, 2]
+    u = x @ Wr.t()                                             # [1024, 2]
+    z_eng = Wc @ u + bc[:, None] * Wr.sum(1)[None, :] + br[None, :]
+    assert z_pub.shape == z_eng.shape == (256, 2)
+    assert float((z_pub - z_eng).abs().max()) < 1e-10 * max(1.0, float(z_pub.abs().max()))
